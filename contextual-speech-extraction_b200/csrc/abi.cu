@@ -1,0 +1,483 @@
+// abi.cu — extern "C" boundary (include/cse_b200.h) and the host-side orchestration of the path.
+//
+// cse_forward is Sepformer.forward of the reference (ContSep.py:53-100, ContExt.py:54-129,
+// sepformer.py:42-81) with Dual_Path_Model_CSE.forward (ContSep.py:205-268) and
+// Dual_Computation_Block_CSE.forward (ContSep.py:453-533) unrolled into kernel launches on the
+// caller's stream.  No allocation, no synchronisation (except cse_forward_host), no global state
+// besides the TMA descriptor cache in gemm_tc.cu.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cse {
+
+static thread_local char g_err[768] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+int launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int grid = (int)min((size_t)148 * 8, (n + 255) / 256);
+  f32_to_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n);
+  return check_launch("f32_to_bf16_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  cse_shape sh;
+  int n_masks, precision;
+  size_t esz;        // activation element size
+  size_t m_max;      // rows of the larger stack
+  int enc_parts;
+  // byte offsets into the workspace
+  size_t E, En, x0, XA, XB, Ra, Rb, H, QKV, AO, F1, ctok, part, stat, U, V, O, G, MP, frames;
+  size_t h_mix, h_ctx, h_est, h_pred;  // device staging for cse_forward_host
+  size_t total;
+};
+
+static int make_shape(int B, int T, int c, int spk, cse_shape* s) {
+  CSE_REQUIRE(B >= 1 && c >= 0 && spk >= 1, "path_shape: need B >= 1, c >= 0, spk >= 1 (B=%d c=%d spk=%d)", B, c, spk);
+  CSE_REQUIRE(T >= kEncK, "path_shape: mixture of %d samples is shorter than the %d-tap encoder kernel", T, kEncK);
+  s->B = B; s->T = T; s->c = c; s->spk = spk;
+  s->L = (T - kEncK) / kEncS + 1;
+  s->gap = kK - (kP + s->L % kK) % kK;
+  s->S = 2 * (s->L + s->gap + kP) / kK;
+  s->T_est = kEncS * (s->L - 1) + kEncK;
+  CSE_REQUIRE(s->S + c <= 2500 && kK + c <= 2500,
+              "path_shape: %d tokens exceed the positional table (2500)", s->S + c);
+  return 0;
+}
+
+static int make_plan(int B, int T, int c, int n_masks, int precision, Plan* p) {
+  if (make_shape(B, T, c, n_masks, &p->sh)) return 1;
+  CSE_REQUIRE(precision == CSE_FP32 || precision == CSE_BF16, "unknown precision %d", precision);
+  p->n_masks = n_masks;
+  p->precision = precision;
+  p->esz = precision == CSE_BF16 ? 2 : 4;
+  const cse_shape& s = p->sh;
+  const size_t rows_i = (size_t)B * s.S * (kK + c), rows_e = (size_t)B * kK * (s.S + c);
+  p->m_max = rows_i > rows_e ? rows_i : rows_e;
+  p->enc_parts = encoder_parts(s.L);
+  const size_t BL = (size_t)B * s.L, chunk = (size_t)B * s.S * kK, Mh = BL * n_masks;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  p->E = take(BL * kN * p->esz);
+  p->En = take(BL * kN * p->esz);
+  p->x0 = take(BL * kN * 4);
+  p->XA = take(chunk * kN * 4);
+  p->XB = take(chunk * kN * 4);
+  p->Ra = take(rows_i * kN * 4);
+  p->Rb = take(rows_e * kN * 4);
+  p->H = take(p->m_max * kN * p->esz);
+  p->QKV = take(p->m_max * 3 * kN * p->esz);   // QKV and AO are contiguous: together they hold F1
+  p->AO = take(p->m_max * kN * p->esz);
+  p->F1 = p->QKV;
+  p->ctok = take((size_t)4 * B * (c > 0 ? c : 1) * kN * 4);
+  const int parts = p->enc_parts > kFinishParts ? p->enc_parts : kFinishParts;
+  p->part = take((size_t)B * parts * 2 * 4);
+  p->stat = take((size_t)B * 2 * 4);
+  p->U = take(BL * kN * p->esz);
+  p->V = take(Mh * kN * p->esz);
+  p->O = take(Mh * kN * p->esz);
+  p->G = take(Mh * kN * p->esz);
+  p->MP = take(Mh * kN * p->esz);
+  p->frames = take(Mh * kEncK * 4);
+  p->h_mix = take((size_t)B * T * 4);
+  p->h_ctx = take((size_t)B * (c > 0 ? c : 1) * CSE_CTX * 4);
+  p->h_est = take((size_t)B * T * n_masks * 4);
+  p->h_pred = take((size_t)B * kN * 4);
+  p->total = off;
+  // F1 [m_max,1024] must fit in QKV+AO: the two takes are adjacent only if no padding was inserted
+  if (p->AO != p->QKV + align_up(p->m_max * 3 * kN * p->esz, 256) ||
+      (p->m_max * 3 * kN * p->esz) % 256 != 0) {
+    // fall back to a dedicated F1 buffer
+    p->F1 = take(p->m_max * kFfn * p->esz);
+    p->total = off;
+  }
+  return 0;
+}
+
+static int linear(const Plan& pl, const void* A, int lda, const float* W32, const void* W16,
+                  const float* bias, float bias_scale, const float* residual, void* C, int ldc,
+                  int M, int N, int K, int relu, int out_fp32, cudaStream_t st) {
+  if (pl.precision == CSE_BF16) {
+    CSE_REQUIRE(W16 != nullptr, "bf16 weights missing: call cse_pack_bf16 first");
+    return launch_gemm_tc((const bf16*)A, lda, (const bf16*)W16, bias, bias_scale, residual, C, ldc,
+                          M, N, K, relu, out_fp32, st);
+  }
+  return launch_gemm_simt((const float*)A, lda, W32, bias, bias_scale, residual, (float*)C, ldc, M,
+                          N, K, relu, st);
+}
+
+// SBTransformerBlock_CSE body after the PE add: 8 pre-norm layers on the fp32 residual stream R
+// (TransformerEncoderLayer.forward, CSE_transformer.py:385-416).  The final LayerNorm belongs to
+// the stack tail (stack_finish / pred_head).
+static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int nseq, int n,
+                     char* ws, cudaStream_t st) {
+  const int M = nseq * n;
+  void* H = ws + pl.H;
+  void* QKV = ws + pl.QKV;
+  void* AO = ws + pl.AO;
+  void* F1 = ws + pl.F1;
+  const int act = pl.precision;
+  for (int l = 0; l < CSE_LAYERS; ++l) {
+    const cse_layer_params& lp = sp.layer[l];
+    if (launch_layernorm(R, lp.ln1_g, lp.ln1_b, M, 1e-6f, act, H, st)) return 1;
+    if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
+               3 * kN, kN, 0, 0, st)) return 1;
+    if (launch_attention(QKV, nseq, n, act, AO, st)) return 1;
+    if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
+               0, 1, st)) return 1;
+    if (launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+    if (linear(pl, H, kN, lp.ffn1_w, lp.ffn1_w_bf16, lp.ffn1_b, 1.f, nullptr, F1, kFfn, M, kFfn, kN, 1,
+               0, st)) return 1;
+    if (linear(pl, F1, kFfn, lp.ffn2_w, lp.ffn2_w_bf16, lp.ffn2_b, 1.f, R, R, kN, M, kN, kFfn, 0, 1,
+               st)) return 1;
+  }
+  return 0;
+}
+
+// Dual_Path_Model_CSE.forward (ContSep.py:205-268) on channels-last mix_w `E` whose masknet.norm
+// partial statistics are already in ws+part (n_parts per sample).  Leaves the pre-ReLU mask
+// [B*L*n_masks, 256] (row = (b,l,s)) in ws+MP.
+static int masknet_impl(const cse_params* p, const void* E, int n_parts, const float* ctx,
+                        const Plan& pl, float* pred_head, char* ws, cudaStream_t st) {
+  const cse_shape& s = pl.sh;
+  const int B = s.B, c = s.c, L = s.L, S = s.S, n_masks = pl.n_masks, act = pl.precision;
+  void* En = ws + pl.En;
+  float* x0 = (float*)(ws + pl.x0);
+  float* XA = (float*)(ws + pl.XA);
+  float* XB = (float*)(ws + pl.XB);
+  float* Ra = (float*)(ws + pl.Ra);
+  float* Rb = (float*)(ws + pl.Rb);
+  float* part = (float*)(ws + pl.part);
+  float* stat = (float*)(ws + pl.stat);
+  float* ctok = (float*)(ws + pl.ctok);
+  const size_t ctok_stride = (size_t)B * (c > 0 ? c : 1) * kN;
+  auto tok = [&](int blk, int inter) -> float* {
+    return c > 0 ? ctok + (size_t)(blk * 2 + inter) * ctok_stride : nullptr;
+  };
+
+  // masknet.norm + masknet.conv1d + segmentation (ContSep.py:226-236)
+  if (launch_gn_finalize(part, B, n_parts, (double)L * kN, 1e-8f, stat, st)) return 1;
+  if (launch_gn_apply(E, stat, p->norm_g, p->norm_b, B, L, act, En, st)) return 1;
+  if (linear(pl, En, kN, p->conv1d_w, p->conv1d_w_bf16, nullptr, 0.f, nullptr, x0, kN, B * L, kN, kN, 0,
+             1, st)) return 1;
+  if (launch_segment(x0, B, L, S, XA, st)) return 1;
+
+  // context prompt tokens of both blocks (ContSep.py:480,511)
+  if (c > 0) {
+    CSE_REQUIRE(ctx != nullptr, "forward: c=%d but ctx is NULL", c);
+    for (int blk = 0; blk < CSE_BLOCKS; ++blk) {
+      const cse_block_params& bp = p->block[blk];
+      CSE_REQUIRE(bp.intra_map_w && bp.inter_map_w && bp.intra_map_b && bp.inter_map_b,
+                  "forward: context mappers missing (model built without add_ctx()?)");
+      if (launch_context_map(ctx, bp.intra_map_w, bp.intra_map_b, B * c, CSE_CTX, tok(blk, 0), st)) return 1;
+      if (launch_context_map(ctx, bp.inter_map_w, bp.inter_map_b, B * c, CSE_CTX, tok(blk, 1), st)) return 1;
+    }
+  }
+
+  if (launch_build_sequences(XA, tok(0, 0), p->block[0].intra.pe, B, S, c, 0, Ra, st)) return 1;
+  for (int blk = 0; blk < CSE_BLOCKS; ++blk) {
+    const cse_block_params& bp = p->block[blk];
+    // intra: sequences = chunks (ContSep.py:474-502)
+    if (run_stack(pl, bp.intra, Ra, B * S, kK + c, ws, st)) return 1;
+    if (launch_stack_finish(Ra, bp.intra.final_g, bp.intra.final_b, bp.intra_norm_g, bp.intra_norm_b, XA,
+                            B, S, c, 0, XB, Rb, bp.inter.pe, tok(blk, 1), part, stat, st)) return 1;
+    // inter: sequences = in-chunk positions (ContSep.py:506-531)
+    if (run_stack(pl, bp.inter, Rb, B * kK, S + c, ws, st)) return 1;
+    const bool last = blk == CSE_BLOCKS - 1;
+    if (last && pred_head != nullptr) {
+      if (launch_pred_head(Rb, bp.inter.final_g, bp.inter.final_b, B, S, c, pred_head, st)) return 1;
+    }
+    if (launch_stack_finish(Rb, bp.inter.final_g, bp.inter.final_b, bp.inter_norm_g, bp.inter_norm_b, XB,
+                            B, S, c, 1, XA, last ? nullptr : Ra,
+                            last ? nullptr : p->block[blk + 1].intra.pe,
+                            last ? nullptr : tok(blk + 1, 0), part, stat, st)) return 1;
+  }
+
+  // mask head (ContSep.py:244-266) with the overlap-add commuted in front of conv2d
+  void* U = ws + pl.U;
+  void* V = ws + pl.V;
+  void* O = ws + pl.O;
+  void* G = ws + pl.G;
+  void* MP = ws + pl.MP;
+  const int Mh = B * L * n_masks;
+  if (launch_prelu_ola(XA, p->prelu, B, S, L, act, U, st)) return 1;
+  if (linear(pl, U, kN, p->conv2d_w, p->conv2d_w_bf16, p->conv2d_b, 2.f, nullptr, V, n_masks * kN, B * L,
+             n_masks * kN, kN, 0, 0, st)) return 1;
+  if (linear(pl, V, kN, p->out_w, p->out_w_bf16, p->out_b, 1.f, nullptr, O, kN, Mh, kN, kN, 0, 0, st)) return 1;
+  if (linear(pl, V, kN, p->gate_w, p->gate_w_bf16, p->gate_b, 1.f, nullptr, G, kN, Mh, kN, kN, 0, 0, st)) return 1;
+  if (launch_gate(O, G, (size_t)Mh * kN, act, O, st)) return 1;
+  if (linear(pl, O, kN, p->end_w, p->end_w_bf16, nullptr, 0.f, nullptr, MP, kN, Mh, kN, kN, 0, 0, st)) return 1;
+  return 0;
+}
+
+static int forward_impl(const cse_params* p, const float* mix, const float* ctx, const Plan& pl,
+                        float* est, float* pred_head, char* ws, cudaStream_t st) {
+  const cse_shape& s = pl.sh;
+  void* E = ws + pl.E;
+  // encoder (ContSep.py:69) with the masknet.norm partial sums fused in
+  if (launch_encoder(mix, p->enc_w, s.B, s.T, s.L, pl.precision, E, (float*)(ws + pl.part), pl.enc_parts, st))
+    return 1;
+  if (masknet_impl(p, E, pl.enc_parts, ctx, pl, pred_head, ws, st)) return 1;
+  // relu(mask) * mix_w -> ConvTranspose1d -> pad / trim (ContSep.py:263,79-95)
+  return launch_mask_decode(ws + pl.MP, E, p->dec_w, s.B, s.L, s.T, pl.n_masks, pl.precision,
+                            (float*)(ws + pl.frames), est, st);
+}
+
+}  // namespace cse
+
+using namespace cse;
+
+extern "C" {
+
+int cse_version(void) { return 100; }
+
+const char* cse_last_error(void) { return g_err; }
+
+int cse_path_shape(int B, int T, int c, int spk, cse_shape* out) {
+  CSE_REQUIRE(out != nullptr, "path_shape: out is NULL");
+  return make_shape(B, T, c, spk, out);
+}
+
+size_t cse_workspace_bytes(int B, int T, int c, int n_masks, int precision) {
+  Plan pl;
+  if (make_plan(B, T, c, n_masks, precision, &pl)) return 0;
+  return pl.total;
+}
+
+size_t cse_pack_bf16_elems(int n_masks) {
+  const size_t per_layer = (size_t)3 * kN * kN + kN * kN + 2 * (size_t)kFfn * kN;
+  return per_layer * CSE_LAYERS * 2 * CSE_BLOCKS + (size_t)kN * kN * 4 + (size_t)n_masks * kN * kN;
+}
+
+int cse_pack_bf16(cse_params* p, int n_masks, void* packed, size_t packed_elems, void* stream) {
+  CSE_REQUIRE(p != nullptr && packed != nullptr, "pack_bf16: NULL argument");
+  CSE_REQUIRE(packed_elems >= cse_pack_bf16_elems(n_masks), "pack_bf16: buffer too small (%zu < %zu)",
+              packed_elems, cse_pack_bf16_elems(n_masks));
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* dst = (bf16*)packed;
+  auto conv = [&](const float* src, size_t n, const void** out) -> int {
+    if (src == nullptr) { set_error("pack_bf16: a weight pointer is NULL"); return 1; }
+    if (launch_f32_to_bf16(src, dst, n, st)) return 1;
+    *out = dst;
+    dst += n;
+    return 0;
+  };
+  for (int b = 0; b < CSE_BLOCKS; ++b) {
+    for (int path = 0; path < 2; ++path) {
+      cse_stack_params& sp = path ? p->block[b].inter : p->block[b].intra;
+      for (int l = 0; l < CSE_LAYERS; ++l) {
+        cse_layer_params& lp = sp.layer[l];
+        if (conv(lp.in_proj_w, (size_t)3 * kN * kN, &lp.in_proj_w_bf16)) return 1;
+        if (conv(lp.out_proj_w, (size_t)kN * kN, &lp.out_proj_w_bf16)) return 1;
+        if (conv(lp.ffn1_w, (size_t)kFfn * kN, &lp.ffn1_w_bf16)) return 1;
+        if (conv(lp.ffn2_w, (size_t)kFfn * kN, &lp.ffn2_w_bf16)) return 1;
+      }
+    }
+  }
+  if (conv(p->conv1d_w, (size_t)kN * kN, &p->conv1d_w_bf16)) return 1;
+  if (conv(p->conv2d_w, (size_t)n_masks * kN * kN, &p->conv2d_w_bf16)) return 1;
+  if (conv(p->out_w, (size_t)kN * kN, &p->out_w_bf16)) return 1;
+  if (conv(p->gate_w, (size_t)kN * kN, &p->gate_w_bf16)) return 1;
+  if (conv(p->end_w, (size_t)kN * kN, &p->end_w_bf16)) return 1;
+  return 0;
+}
+
+int cse_forward(const cse_params* p, const float* mix, const float* ctx, int B, int T, int c,
+                int n_masks, int precision, float* est, float* pred_head, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  CSE_REQUIRE(p && mix && est && workspace, "forward: NULL argument");
+  Plan pl;
+  if (make_plan(B, T, c, n_masks, precision, &pl)) return 1;
+  CSE_REQUIRE(workspace_bytes >= pl.total, "forward: workspace too small (%zu < %zu bytes)",
+              workspace_bytes, pl.total);
+  CSE_REQUIRE(((uintptr_t)workspace & 255) == 0, "forward: workspace must be 256-byte aligned");
+  return forward_impl(p, mix, ctx, pl, est, pred_head, (char*)workspace, (cudaStream_t)stream);
+}
+
+int cse_forward_host(const cse_params* p, const float* mix_host, const float* ctx_host, int B, int T,
+                     int c, int n_masks, int precision, float* est_host, float* pred_head_host,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  CSE_REQUIRE(p && mix_host && est_host && workspace, "forward_host: NULL argument");
+  Plan pl;
+  if (make_plan(B, T, c, n_masks, precision, &pl)) return 1;
+  CSE_REQUIRE(workspace_bytes >= pl.total, "forward_host: workspace too small (%zu < %zu bytes)",
+              workspace_bytes, pl.total);
+  CSE_REQUIRE(((uintptr_t)workspace & 255) == 0, "forward_host: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* d_mix = (float*)(ws + pl.h_mix);
+  float* d_ctx = (float*)(ws + pl.h_ctx);
+  float* d_est = (float*)(ws + pl.h_est);
+  float* d_pred = (float*)(ws + pl.h_pred);
+  CSE_CUDA(cudaMemcpyAsync(d_mix, mix_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
+  if (c > 0) {
+    CSE_REQUIRE(ctx_host != nullptr, "forward_host: c=%d but ctx is NULL", c);
+    CSE_CUDA(cudaMemcpyAsync(d_ctx, ctx_host, (size_t)B * c * CSE_CTX * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (forward_impl(p, d_mix, c > 0 ? d_ctx : nullptr, pl, d_est, pred_head_host ? d_pred : nullptr, ws, st))
+    return 1;
+  CSE_CUDA(cudaMemcpyAsync(est_host, d_est, (size_t)B * T * n_masks * 4, cudaMemcpyDeviceToHost, st));
+  if (pred_head_host)
+    CSE_CUDA(cudaMemcpyAsync(pred_head_host, d_pred, (size_t)B * kN * 4, cudaMemcpyDeviceToHost, st));
+  CSE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int cse_masknet_fwd(const cse_params* p, const void* E, const float* ctx, int B, int L, int c,
+                    int n_masks, int precision, float* mask, float* pred_head, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  CSE_REQUIRE(p && E && mask && workspace, "masknet_fwd: NULL argument");
+  CSE_REQUIRE(L >= 1, "masknet_fwd: L must be >= 1");
+  Plan pl;
+  if (make_plan(B, kEncS * (L - 1) + kEncK, c, n_masks, precision, &pl)) return 1;
+  CSE_REQUIRE(workspace_bytes >= pl.total, "masknet_fwd: workspace too small (%zu < %zu bytes)",
+              workspace_bytes, pl.total);
+  CSE_REQUIRE(((uintptr_t)workspace & 255) == 0, "masknet_fwd: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  if (launch_gn_stats(E, B, L, precision, (float*)(ws + pl.part), kFinishParts, st)) return 1;
+  if (masknet_impl(p, E, kFinishParts, ctx, pl, pred_head, ws, st)) return 1;
+  return launch_relu_f32(ws + pl.MP, (size_t)B * L * n_masks * kN, precision, mask, st);
+}
+
+// ---- per-stage entry points ----
+int cse_encoder_fwd(const float* mix, const float* w, int B, int T, int act_dtype, void* out,
+                    float* gn_part, int* n_parts, void* stream) {
+  CSE_REQUIRE(mix && w && out && gn_part, "encoder_fwd: NULL argument");
+  cse_shape s;
+  if (make_shape(B, T, 0, 1, &s)) return 1;
+  const int parts = encoder_parts(s.L);
+  if (n_parts) *n_parts = parts;
+  return launch_encoder(mix, w, B, T, s.L, act_dtype, out, gn_part, parts, (cudaStream_t)stream);
+}
+
+int cse_gn_finalize(const float* gn_part, int B, int n_parts, double count, float eps, float* stat,
+                    void* stream) {
+  CSE_REQUIRE(gn_part && stat && B > 0 && n_parts > 0, "gn_finalize: bad argument");
+  return launch_gn_finalize(gn_part, B, n_parts, count, eps, stat, (cudaStream_t)stream);
+}
+
+int cse_gn_apply(const void* x, const float* stat, const float* g, const float* b, int B, int L,
+                 int act_dtype, void* out, void* stream) {
+  CSE_REQUIRE(x && stat && g && b && out, "gn_apply: NULL argument");
+  return launch_gn_apply(x, stat, g, b, B, L, act_dtype, out, (cudaStream_t)stream);
+}
+
+int cse_linear(const void* A, int lda, const void* W, const float* bias, float bias_scale,
+               const float* residual, void* C, int ldc, int M, int N, int K, int relu, int out_fp32,
+               int precision, void* stream) {
+  CSE_REQUIRE(A && W && C, "linear: NULL argument");
+  if (precision == CSE_BF16)
+    return launch_gemm_tc((const bf16*)A, lda, (const bf16*)W, bias, bias_scale, residual, C, ldc, M,
+                          N, K, relu, out_fp32, (cudaStream_t)stream);
+  CSE_REQUIRE(precision == CSE_FP32, "linear: unknown precision %d", precision);
+  return launch_gemm_simt((const float*)A, lda, (const float*)W, bias, bias_scale, residual, (float*)C,
+                          ldc, M, N, K, relu, (cudaStream_t)stream);
+}
+
+int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps, int act_dtype,
+                      void* out, void* stream) {
+  CSE_REQUIRE(x && g && b && out, "layernorm_fwd: NULL argument");
+  return launch_layernorm(x, g, b, M, eps, act_dtype, out, (cudaStream_t)stream);
+}
+
+int cse_attention_fwd(const void* qkv, int nseq, int n, int act_dtype, void* out, void* stream) {
+  CSE_REQUIRE(qkv && out, "attention_fwd: NULL argument");
+  return launch_attention(qkv, nseq, n, act_dtype, out, (cudaStream_t)stream);
+}
+
+int cse_segment(const float* x0, int B, int L, int S, float* X, void* stream) {
+  CSE_REQUIRE(x0 && X, "segment: NULL argument");
+  return launch_segment(x0, B, L, S, X, (cudaStream_t)stream);
+}
+
+int cse_build_sequences(const float* X, const float* ctok, const float* pe, int B, int S, int c,
+                        int inter, float* R, void* stream) {
+  CSE_REQUIRE(X && pe && R && (c == 0 || ctok), "build_sequences: NULL argument");
+  return launch_build_sequences(X, ctok, pe, B, S, c, inter, R, (cudaStream_t)stream);
+}
+
+int cse_context_map(const float* ctx, const float* w, const float* b, int rows, int in_dim, float* out,
+                    void* stream) {
+  CSE_REQUIRE(ctx && w && b && out, "context_map: NULL argument");
+  return launch_context_map(ctx, w, b, rows, in_dim, out, (cudaStream_t)stream);
+}
+
+int cse_stack_finish(const float* R, const float* ln_g, const float* ln_b, const float* gn_g,
+                     const float* gn_b, const float* skip, int B, int S, int c, int inter, float* out,
+                     float* gn_part, float* stat, void* stream) {
+  CSE_REQUIRE(R && ln_g && ln_b && gn_g && gn_b && skip && out && gn_part && stat, "stack_finish: NULL argument");
+  return launch_stack_finish(R, ln_g, ln_b, gn_g, gn_b, skip, B, S, c, inter, out, nullptr, nullptr,
+                             nullptr, gn_part, stat, (cudaStream_t)stream);
+}
+
+int cse_pred_head(const float* R_inter, const float* ln_g, const float* ln_b, int B, int S, int c,
+                  float* pred_head, void* stream) {
+  CSE_REQUIRE(R_inter && ln_g && ln_b && pred_head, "pred_head: NULL argument");
+  return launch_pred_head(R_inter, ln_g, ln_b, B, S, c, pred_head, (cudaStream_t)stream);
+}
+
+int cse_prelu_overlap_add(const float* X, const float* prelu, int B, int S, int L, int act_dtype, void* U,
+                          void* stream) {
+  CSE_REQUIRE(X && prelu && U, "prelu_overlap_add: NULL argument");
+  return launch_prelu_ola(X, prelu, B, S, L, act_dtype, U, (cudaStream_t)stream);
+}
+
+int cse_gate(const void* o, const void* g, size_t n, int act_dtype, void* out, void* stream) {
+  CSE_REQUIRE(o && g && out, "gate: NULL argument");
+  return launch_gate(o, g, n, act_dtype, out, (cudaStream_t)stream);
+}
+
+int cse_mask_decode(const void* mask_pre, const void* E, const float* dec_w, int B, int L, int T,
+                    int n_masks, int act_dtype, float* frames, float* est, void* stream) {
+  CSE_REQUIRE(mask_pre && dec_w && frames && est, "mask_decode: NULL argument");  // E may be NULL
+  return launch_mask_decode(mask_pre, E, dec_w, B, L, T, n_masks, act_dtype, frames, est,
+                            (cudaStream_t)stream);
+}
+
+int cse_si_snr(const float* source, const float* estimate, int B, int T, int C, float* out, void* stream) {
+  CSE_REQUIRE(source && estimate && out && B > 0 && T > 0, "si_snr: bad argument");
+  return launch_si_snr(source, estimate, B, T, C, out, (cudaStream_t)stream);
+}
+
+int cse_pit_si_snr(const float* source, const float* estimate_source, int B, int T, int C, float* loss,
+                   int* perm, void* stream) {
+  CSE_REQUIRE(source && estimate_source && loss && perm && B > 0 && T > 0, "pit_si_snr: bad argument");
+  return launch_pit(source, estimate_source, B, T, C, loss, perm, (cudaStream_t)stream);
+}
+
+int cse_tm_si_snr(const float* preds, const float* target, int B, int T, float* out, void* stream) {
+  CSE_REQUIRE(preds && target && out && B > 0 && T > 0, "tm_si_snr: bad argument");
+  return launch_tm_si_snr(preds, target, B, T, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// common.cuh — shared device/host helpers for the sm_100a Sepformer kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cse_b200.h"
+
+namespace cse {
+
+constexpr int kN = CSE_N;          // 256 channels
+constexpr int kK = CSE_K;          // 250 frames per chunk
+constexpr int kP = CSE_K / 2;      // hop
+constexpr int kHeads = CSE_HEADS;  // 8
+constexpr int kDh = CSE_N / CSE_HEADS;  // 32
+constexpr int kFfn = CSE_FFN;
+constexpr int kEncK = 16;
+constexpr int kEncS = 8;
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (abi.cu owns the thread-local buffer) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define CSE_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      cse::set_error(__VA_ARGS__);      \
+      return 1;                         \
+    }                                   \
+  } while (0)
+
+#define CSE_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      cse::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                           \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+
+// ---- activation load/store: 8 consecutive channels per lane (256 = 32 lanes x 8) ----
+struct f8 {
+  float v[8];
+};
+
+__device__ __forceinline__ f8 ld8(const float* p) {
+  f8 r;
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ f8 ld8(const bf16* p) {
+  f8 r;
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(float* p, const f8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const f8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+// value after a store/load round trip through the activation type
+template <typename T> __device__ __forceinline__ float round_act(float x) { return to_f(from_f<T>(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Row LayerNorm of 256 channels held as 8 per lane; two-pass (mean, then centred variance).
+__device__ __forceinline__ void ln_row(f8& x, const f8& g, const f8& b, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x.v[i];
+  const float mean = warp_sum(s) * (1.0f / kN);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x.v[i] -= mean;
+    q += x.v[i] * x.v[i];
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kN) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x.v[i] = x.v[i] * rstd * g.v[i] + b.v[i];
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- kernel launchers shared between translation units (defined in the named .cu) ----
+// frontend.cu
+int launch_encoder(const float* mix, const float* w, int B, int T, int L, int act, void* out,
+                   float* gn_part, int n_parts, cudaStream_t st);
+int encoder_parts(int L);
+int launch_gn_finalize(const float* part, int B, int n_parts, double count, float eps, float* stat,
+                       cudaStream_t st);
+int launch_gn_stats(const void* x, int B, int rows, int act, float* gn_part, int n_parts,
+                    cudaStream_t st);
+int launch_gn_apply(const void* x, const float* stat, const float* g, const float* b, int B, int L,
+                    int act, void* out, cudaStream_t st);
+int launch_segment(const float* x0, int B, int L, int S, float* X, cudaStream_t st);
+int launch_build_sequences(const float* X, const float* ctok, const float* pe, int B, int S, int c,
+                           int inter, float* R, cudaStream_t st);
+int launch_context_map(const float* ctx, const float* w, const float* b, int rows, int in_dim,
+                       float* out, cudaStream_t st);
+// norm.cu
+int launch_layernorm(const float* x, const float* g, const float* b, int M, float eps, int act,
+                     void* out, cudaStream_t st);
+constexpr int kFinishParts = 64;  // GroupNorm partials per sample in stack_finish
+int launch_stack_finish(const float* R, const float* ln_g, const float* ln_b, const float* gn_g,
+                        const float* gn_b, const float* skip, int B, int S, int c, int inter,
+                        float* out, float* next_R, const float* next_pe, const float* next_ctok,
+                        float* gn_part, float* stat, cudaStream_t st);
+int launch_pred_head(const float* R, const float* ln_g, const float* ln_b, int B, int S, int c,
+                     float* out, cudaStream_t st);
+// gemm_simt.cu / gemm_tc.cu
+int launch_gemm_simt(const float* A, int lda, const float* W, const float* bias, float bias_scale,
+                     const float* residual, float* C, int ldc, int M, int N, int K, int relu,
+                     cudaStream_t st);
+int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, float bias_scale,
+                   const float* residual, void* C, int ldc, int M, int N, int K, int relu,
+                   int out_fp32, cudaStream_t st);
+// attention.cu
+int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaStream_t st);
+// head.cu
+int launch_prelu_ola(const float* X, const float* prelu, int B, int S, int L, int act, void* U,
+                     cudaStream_t st);
+int launch_gate(const void* o, const void* g, size_t n, int act, void* out, cudaStream_t st);
+int launch_relu_f32(const void* x, size_t n, int act, float* out, cudaStream_t st);
+int launch_mask_decode(const void* mask_pre, const void* E, const float* dec_w, int B, int L, int T,
+                       int n_masks, int act, float* frames, float* est, cudaStream_t st);
+// loss.cu
+int launch_si_snr(const float* source, const float* estimate, int B, int T, int C, float* out,
+                  cudaStream_t st);
+int launch_pit(const float* source, const float* est, int B, int T, int C, float* loss, int* perm,
+               cudaStream_t st);
+int launch_tm_si_snr(const float* preds, const float* target, int B, int T, float* out,
+                     cudaStream_t st);
+// pack.cu (in abi.cu)
+int launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
+
+}  // namespace cse

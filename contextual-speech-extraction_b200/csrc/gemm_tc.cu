@@ -1,0 +1,455 @@
+// gemm_tc.cu — bf16 tensor-core GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM.
+//
+// C[M,N] = A[M,K] * W[N,K]^T (+ bias_scale*bias)(relu)(+ residual): every nn.Linear / 1x1 conv of
+// the path in CSE_BF16 mode (QKV, out-proj, FFN1/2: CSE_transformer.py:335-340,547;
+// masknet.conv1d/conv2d/output/output_gate/end_conv1x1: ContSep.py:229,247,255,258).
+// A is row-major activations, W is the nn.Linear weight [out,in]: BOTH are K-major, which is the
+// native UMMA operand layout, so no transposes exist anywhere.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      : TMA producer — 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B,
+//                 mbarrier complete_tx
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
+//                 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the
+//                 MMAs of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32 columns), bias / ReLU / fp32 residual,
+//                 vector stores (one output row per thread)
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace cse {
+
+constexpr int kTM = 128;  // UMMA M
+constexpr int kTK = 64;   // K per stage: 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait (~2 s at 2 GHz): a broken pipeline traps with a message instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("gemm_tc: mbarrier timeout (tag %d, block %d, thread %d, parity %u)\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
+               "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1)
+// | [32,46) SBO>>4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32 (cute::UMMA::InstrDescriptor):
+// c_format=1 @4, a_format=1 @7, b_format=1 @10, a_major=0 @15, b_major=0 @16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kTK * 2;   // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256;
+};
+
+template <int BN, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, float bias_scale, const float* residual, void* Cout,
+               int ldc, int M, int N, int K, int relu) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + Cfg::kStages * Cfg::kABytes;
+  const uint32_t sBar = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  const uint32_t bar_full = sBar;
+  const uint32_t bar_empty = sBar + 8 * Cfg::kStages;
+  const uint32_t bar_tfull = sBar + 16 * Cfg::kStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + kTM - 1) / kTM, n_tiles = N / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = K / kTK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    // The whole warp walks the loop (keeps it convergent for the teardown barrier); lane 0 acts.
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (lane == 0) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+          mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, bar_full + 8 * stage, kb * kTK, m0);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, bar_full + 8 * stage, kb * kTK, n0);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
+    constexpr uint32_t idesc = make_idesc_bf16(kTM, BN);
+    uint32_t stage = 0, phase = 0, astage = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (lane == 0) {
+        mbar_wait(bar_tempty + 8 * astage, aphase ^ 1, 2);
+        tc_fence_after();
+      }
+      __syncwarp();
+      const uint32_t d_tmem = tmem_base + astage * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (lane == 0) {
+          mbar_wait(bar_full + 8 * stage, phase, 3);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::kABytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kTK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) umma_commit(bar_tfull + 8 * astage);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++astage == 2) { astage = 0; aphase ^= 1; }
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    uint32_t astage = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
+      const int row = m0 + quarter * 32 + lane;
+      mbar_wait(bar_tfull + 8 * astage, aphase, 4);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + astage * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float v[32];
+        tmem_ld32(t_row + cc * 32, v);
+        const int col0 = n0 + cc * 32;
+        if (bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+            v[i] = fmaf(bias_scale, b4.x, v[i]);
+            v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
+            v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
+            v[i + 3] = fmaf(bias_scale, b4.w, v[i + 3]);
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (row < M) {
+          if constexpr (OUT_F32) {
+            float* crow = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + col0;
+            if (residual != nullptr) {
+              const float* rrow = residual + (size_t)row * ldc + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rrow + i);
+                v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            bf16* crow = reinterpret_cast<bf16*>(Cout) + (size_t)row * ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              h[0] = __floats2bfloat162_rn(v[i], v[i + 1]);
+              h[1] = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              h[2] = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+              h[3] = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(crow + i) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * astage);
+      if (++astage == 2) { astage = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point fetched through cudart; no libcuda link dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull + k.box_rows);
+    return h;
+  }
+};
+
+// bf16 row-major [rows, cols] matrix with leading dimension ld; box = [box_rows x 64 cols], 128B swizzle.
+static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)kTK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box_rows=%u",
+              (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols,
+              (unsigned long long)ld, box_rows);
+    return 1;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool OUT_F32>
+static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+                          float bias_scale, const float* residual, void* C, int ldc, int M, int N,
+                          int K, int relu, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  const int tiles = ceil_div(M, kTM) * (N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, bias, bias_scale,
+                                                                      residual, C, ldc, M, N, K, relu);
+  return check_launch("gemm_tc_kernel");
+}
+
+int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, float bias_scale,
+                   const float* residual, void* C, int ldc, int M, int N, int K, int relu,
+                   int out_fp32, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (K % kTK != 0 || N % 128 != 0 || lda % 8 != 0 || (ldc % 8) != 0) {
+    set_error("gemm_tc: need K %% 64 == 0, N %% 128 == 0, lda/ldc %% 8 == 0 (M=%d N=%d K=%d lda=%d ldc=%d)",
+              M, N, K, lda, ldc);
+    return 1;
+  }
+  if (residual != nullptr && !out_fp32) {
+    set_error("gemm_tc: a residual needs an fp32 output");
+    return 1;
+  }
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) {
+    set_error("gemm_tc: operands must be 16-byte aligned");
+    return 1;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, &tmA)) return 1;
+  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, &tmB)) return 1;
+  if (BN == 256) {
+    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st);
+  }
+  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st)
+                  : launch_tc_impl<128, false>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st);
+}
+
+}  // namespace cse

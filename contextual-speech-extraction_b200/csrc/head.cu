@@ -1,0 +1,201 @@
+// head.cu — mask-estimation tail: PReLU + overlap-add, tanh/sigmoid gate, mask*mix_w and the
+// ConvTranspose1d overlap-add decoder (HBM-bound kernels).
+//
+// Reference: Dual_Path_Model_CSE.forward tail (ContSep.py:244-266), _over_add (ContSep.py:337-370),
+// Sepformer.forward mask/decode/length fix (ContSep.py:79-95; ContExt.py:116-129),
+// speechbrain Decoder = nn.ConvTranspose1d(256,1,16,stride=8,bias=False).
+#include "common.cuh"
+
+namespace cse {
+
+// U[b,l,:] = prelu(X[b,s1,k1,:]) + prelu(X[b,s1-1,k1+P,:]),  p = l+P, s1 = p/P, k1 = p - s1*P.
+// (Every kept frame is covered by exactly two chunks because gap >= 1, ContSep.py:287.)
+// The 1x1 conv2d that the reference applies BEFORE the overlap-add is linear and position-wise,
+// so it commutes with it (bias counted twice): this halves the conv2d GEMM rows.
+template <typename T>
+__global__ void __launch_bounds__(256) prelu_ola_kernel(const float* __restrict__ X,
+                                                        const float* __restrict__ prelu, int S,
+                                                        int L, size_t rows, T* __restrict__ U) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  const float a = prelu[0];
+  for (size_t r = warp; r < rows; r += nwarps) {
+    const int l = (int)(r % L);
+    const int b = (int)(r / L);
+    const int p = l + kP;
+    const int s1 = p / kP, k1 = p - s1 * kP;
+    const f8 x1 = ld8(X + (((size_t)b * S + s1) * kK + k1) * kN + lane * 8);
+    const f8 x2 = ld8(X + (((size_t)b * S + s1 - 1) * kK + k1 + kP) * kN + lane * 8);
+    f8 u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y1 = x1.v[i] >= 0.f ? x1.v[i] : a * x1.v[i];
+      const float y2 = x2.v[i] >= 0.f ? x2.v[i] : a * x2.v[i];
+      u.v[i] = y1 + y2;
+    }
+    st8(U + r * kN + lane * 8, u);
+  }
+}
+
+int launch_prelu_ola(const float* X, const float* prelu, int B, int S, int L, int act, void* U,
+                     cudaStream_t st) {
+  const size_t rows = (size_t)B * L;
+  const int grid = (int)min((size_t)148 * 8, (rows + 7) / 8);
+  if (act == CSE_BF16)
+    prelu_ola_kernel<bf16><<<grid, 256, 0, st>>>(X, prelu, S, L, rows, (bf16*)U);
+  else
+    prelu_ola_kernel<float><<<grid, 256, 0, st>>>(X, prelu, S, L, rows, (float*)U);
+  return check_launch("prelu_ola_kernel");
+}
+
+// out = tanh(o) * sigmoid(g), 8 elements per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) gate_kernel(const T* o, const T* g,
+                                                   size_t n8, T* out) {  // out may alias o
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    const f8 a = ld8(o + i * 8), b = ld8(g + i * 8);
+    f8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = tanhf(a.v[k]) * (1.0f / (1.0f + expf(-b.v[k])));
+    st8(out + i * 8, r);
+  }
+}
+
+int launch_gate(const void* o, const void* g, size_t n, int act, void* out, cudaStream_t st) {
+  if (n % 8 != 0) {
+    set_error("gate: element count %zu not a multiple of 8", n);
+    return 1;
+  }
+  const size_t n8 = n / 8;
+  const int grid = (int)min((size_t)148 * 8, (n8 + 255) / 256);
+  if (act == CSE_BF16)
+    gate_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)o, (const bf16*)g, n8, (bf16*)out);
+  else
+    gate_kernel<float><<<grid, 256, 0, st>>>((const float*)o, (const float*)g, n8, (float*)out);
+  return check_launch("gate_kernel");
+}
+
+// frames[r, k] = sum_n relu(mask_pre[r,n]) * E[b,l,n] * dec_w[n,k],  r = (b*L + l)*n_masks + s.
+// One warp per row; the 16 tap sums are reduced with a butterfly that halves the live values at
+// each shuffle step (16 -> 8 -> 4 -> 2 -> 1 per lane), 31 shuffles per row instead of 80.
+template <typename T>
+__global__ void __launch_bounds__(256) decode_frames_kernel(const T* __restrict__ mask_pre,
+                                                            const T* __restrict__ E,
+                                                            const float* __restrict__ dec_w,
+                                                            int n_masks, size_t rows,
+                                                            float* __restrict__ frames) {
+  // taps of channel n = lane*8+i live at s_w[(i*32+lane)*20 + k]: the 20-float lane stride makes
+  // the per-lane float4 reads below bank-conflict-free (a plain [n][16] layout is 32-way conflicted)
+  __shared__ __align__(16) float s_w[kN * 20];
+  for (int idx = threadIdx.x; idx < kN * kEncK; idx += 256) {
+    const int n = idx / kEncK, k = idx % kEncK;
+    s_w[((n & 7) * 32 + (n >> 3)) * 20 + k] = dec_w[idx];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  for (size_t r = warp; r < rows; r += nwarps) {
+    const size_t bl = r / n_masks;
+    const f8 m = ld8(mask_pre + r * kN + lane * 8);
+    f8 e;
+    if (E != nullptr) e = ld8(E + bl * kN + lane * 8);
+    float t[kEncK];
+#pragma unroll
+    for (int k = 0; k < kEncK; ++k) t[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // E == NULL: plain Decoder.forward on an already-masked input (no ReLU, no multiply)
+      const float v = (E != nullptr) ? fmaxf(m.v[i], 0.f) * e.v[i] : m.v[i];
+      const float* wr = s_w + (i * 32 + lane) * 20;
+#pragma unroll
+      for (int k = 0; k < kEncK; k += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+        t[k] = fmaf(v, w4.x, t[k]);
+        t[k + 1] = fmaf(v, w4.y, t[k + 1]);
+        t[k + 2] = fmaf(v, w4.z, t[k + 2]);
+        t[k + 3] = fmaf(v, w4.w, t[k + 3]);
+      }
+    }
+    // butterfly: after the step with offset o, lane keeps the half of the taps selected by its
+    // bit (lane & o); after 4 steps each lane holds one tap summed over its 16-lane half... then
+    // a final xor-16 step adds the two halves.
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      const int o = 1 << step;           // lane bit used at this step
+      const int half = kEncK >> (step + 1);  // values kept
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int k = 0; k < half; ++k) {
+        const float keep = up ? t[k + half] : t[k];
+        const float send = up ? t[k] : t[k + half];
+        t[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    float v = t[0] + __shfl_xor_sync(0xffffffffu, t[0], 16);
+    // lane's tap index: bit(step) of lane selects the upper half at that step
+    // tap = b0*8 + b1*4 + b2*2 + b3 where b_i = bit i of lane
+    const int tap = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+    if (lane < 16) frames[r * kEncK + tap] = v;
+  }
+}
+
+// est[b,t,s] = frames[(b,l,s), t-8l] + frames[(b,l-1,s), t-8(l-1)], l = t/8; zero beyond T_est
+// (F.pad branch, ContSep.py:92-93); only t < T is produced (trim branch, :95).
+__global__ void __launch_bounds__(256) decode_ola_kernel(const float* __restrict__ frames, int L,
+                                                         int T, int n_masks, size_t total,
+                                                         float* __restrict__ est) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int s = (int)(i % n_masks);
+    const size_t bt = i / n_masks;
+    const int t = (int)(bt % T);
+    const size_t b = bt / T;
+    const int l = t >> 3, k = t & 7;
+    float v = 0.f;
+    if (l < L) v += frames[((b * L + l) * n_masks + s) * kEncK + k];
+    if (l >= 1 && l - 1 < L) v += frames[((b * L + l - 1) * n_masks + s) * kEncK + k + 8];
+    est[i] = v;
+  }
+}
+
+// mask = relu(mask_pre) as fp32 (Dual_Path_Model.forward's return value, ContSep.py:263).
+template <typename T>
+__global__ void __launch_bounds__(256) relu_f32_kernel(const T* __restrict__ x, size_t n8,
+                                                       float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    f8 v = ld8(x + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+    st8(out + i * 8, v);
+  }
+}
+
+int launch_relu_f32(const void* x, size_t n, int act, float* out, cudaStream_t st) {
+  const size_t n8 = n / 8;
+  const int grid = (int)min((size_t)148 * 8, (n8 + 255) / 256);
+  if (act == CSE_BF16)
+    relu_f32_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, n8, out);
+  else
+    relu_f32_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n8, out);
+  return check_launch("relu_f32_kernel");
+}
+
+int launch_mask_decode(const void* mask_pre, const void* E, const float* dec_w, int B, int L, int T,
+                       int n_masks, int act, float* frames, float* est, cudaStream_t st) {
+  const size_t rows = (size_t)B * L * n_masks;
+  const int grid = (int)min((size_t)148 * 4, (rows + 7) / 8);
+  if (act == CSE_BF16)
+    decode_frames_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)mask_pre, (const bf16*)E, dec_w,
+                                                     n_masks, rows, frames);
+  else
+    decode_frames_kernel<float><<<grid, 256, 0, st>>>((const float*)mask_pre, (const float*)E,
+                                                      dec_w, n_masks, rows, frames);
+  if (check_launch("decode_frames_kernel")) return 1;
+  const size_t total = (size_t)B * T * n_masks;
+  const int grid2 = (int)min((size_t)148 * 8, (total + 255) / 256);
+  decode_ola_kernel<<<grid2, 256, 0, st>>>(frames, L, T, n_masks, total, est);
+  return check_launch("decode_ola_kernel");
+}
+
+}  // namespace cse

@@ -1,0 +1,192 @@
+// norm.cu — warp-shuffle LayerNorm and the stack tails (final LN -> GroupNorm -> skip -> relayout).
+//
+// Reference: sb LayerNorm = nn.LayerNorm(256, eps 1e-6) (CSE_transformer.py:197,358-359,386,408);
+// Dual_Computation_Block_CSE tails (ContSep.py:487-502 intra, :516-531 inter);
+// pred_head (ContSep.py:516-517).
+#include "common.cuh"
+
+namespace cse {
+
+// One warp per row of 256 fp32 channels (1 KB): 8 channels per lane, two shuffles trees.
+// Algorithmic bytes per row: 1024 in + e*256 out.
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x,
+                                                        const float* __restrict__ g,
+                                                        const float* __restrict__ b, size_t M,
+                                                        float eps, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);
+  for (size_t r = warp; r < M; r += nwarps) {
+    f8 v = ld8(x + r * kN + lane * 8);
+    ln_row(v, gg, bb, eps);
+    st8(out + r * kN + lane * 8, v);
+  }
+}
+
+int launch_layernorm(const float* x, const float* g, const float* b, int M, float eps, int act,
+                     void* out, cudaStream_t st) {
+  const int grid = (int)min((size_t)148 * 8, ((size_t)M + 7) / 8);
+  if (act == CSE_BF16)
+    layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (bf16*)out);
+  else
+    layernorm_kernel<float><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (float*)out);
+  return check_launch("layernorm_kernel");
+}
+
+// --------------------------------------------------------------------------------------------
+// Stack tail, pass 1: GroupNorm statistics of y = LN_final(R) over the non-context rows of each
+// sample.  grid (kFinishParts, B); each warp strides over the sample's rows; deterministic
+// per-CTA partials (no atomics).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t stack_row(int b, int s, int k, int S, int c, int inter) {
+  // row of R that holds chunk s / in-chunk position k of sample b
+  return inter ? ((size_t)b * kK + k) * (size_t)(S + c) + c + s
+               : ((size_t)b * S + s) * (size_t)(kK + c) + c + k;
+}
+
+__global__ void __launch_bounds__(256) finish_stats_kernel(const float* __restrict__ R,
+                                                           const float* __restrict__ ln_g,
+                                                           const float* __restrict__ ln_b, int S,
+                                                           int c, int inter,
+                                                           float* __restrict__ gn_part) {
+  __shared__ float s_red[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const f8 gg = ld8(ln_g + lane * 8), bb = ld8(ln_b + lane * 8);
+  const int rows = S * kK;
+  float sum = 0.f, sq = 0.f;
+  for (int o = blockIdx.x * 8 + wid; o < rows; o += gridDim.x * 8) {
+    const int s = o / kK, k = o % kK;
+    f8 v = ld8(R + stack_row(b, s, k, S, c, inter) * kN + lane * 8);
+    ln_row(v, gg, bb, 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sum += v.v[i];
+      sq += v.v[i] * v.v[i];
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  if (lane == 0) {
+    s_red[0][wid] = sum;
+    s_red[1][wid] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a += s_red[0][i];
+      q += s_red[1][i];
+    }
+    float* p = gn_part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+    p[0] = a;
+    p[1] = q;
+  }
+}
+
+// Pass 2: out[b,s,k] = GN(LN(R row)) * gn_g + gn_b + skip[b,s,k]; optionally also seeds the NEXT
+// stack's residual stream (other layout) with + pe and its context rows, so the chunk tensor is
+// never re-read for the relayout.
+__global__ void __launch_bounds__(256) finish_apply_kernel(
+    const float* __restrict__ R, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+    const float* __restrict__ gn_g, const float* __restrict__ gn_b, const float* __restrict__ skip,
+    const float* __restrict__ stat, int B, int S, int c, int inter, float* __restrict__ out,
+    float* __restrict__ next_R, const float* __restrict__ next_pe,
+    const float* __restrict__ next_ctok) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  const f8 lg = ld8(ln_g + lane * 8), lb = ld8(ln_b + lane * 8);
+  const f8 gg = ld8(gn_g + lane * 8), gb = ld8(gn_b + lane * 8);
+  const size_t rows = (size_t)B * S * kK;
+  const int next_inter = !inter;
+  for (size_t o = warp; o < rows; o += nwarps) {
+    const int k = (int)(o % kK);
+    const size_t bs = o / kK;
+    const int s = (int)(bs % S);
+    const int b = (int)(bs / S);
+    f8 v = ld8(R + stack_row(b, s, k, S, c, inter) * kN + lane * 8);
+    ln_row(v, lg, lb, 1e-6f);
+    const float mean = stat[b * 2], rstd = stat[b * 2 + 1];
+    const f8 sk = ld8(skip + o * kN + lane * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = (v.v[i] - mean) * rstd * gg.v[i] + gb.v[i] + sk.v[i];
+    st8(out + o * kN + lane * 8, v);
+    if (next_R != nullptr) {
+      const int pos = c + (next_inter ? s : k);
+      const f8 p = ld8(next_pe + (size_t)pos * kN + lane * 8);
+      f8 w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w.v[i] = v.v[i] + p.v[i];
+      st8(next_R + stack_row(b, s, k, S, c, next_inter) * kN + lane * 8, w);
+      // the warp that owns the first audio row of a next-stack sequence also writes its prompt
+      const bool first = next_inter ? (s == 0) : (k == 0);
+      if (first) {
+        const size_t base = stack_row(b, s, k, S, c, next_inter) - (size_t)pos;
+        for (int j = 0; j < c; ++j) {
+          f8 t = ld8(next_ctok + ((size_t)b * c + j) * kN + lane * 8);
+          const f8 pj = ld8(next_pe + (size_t)j * kN + lane * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t.v[i] += pj.v[i];
+          st8(next_R + (base + j) * kN + lane * 8, t);
+        }
+      }
+    }
+  }
+}
+
+int launch_stack_finish(const float* R, const float* ln_g, const float* ln_b, const float* gn_g,
+                        const float* gn_b, const float* skip, int B, int S, int c, int inter,
+                        float* out, float* next_R, const float* next_pe, const float* next_ctok,
+                        float* gn_part, float* stat, cudaStream_t st) {
+  dim3 g1(kFinishParts, B);
+  finish_stats_kernel<<<g1, 256, 0, st>>>(R, ln_g, ln_b, S, c, inter, gn_part);
+  if (check_launch("finish_stats_kernel")) return 1;
+  if (launch_gn_finalize(gn_part, B, kFinishParts, (double)S * kK * kN, 1e-8f, stat, st)) return 1;
+  const size_t rows = (size_t)B * S * kK;
+  const int grid = (int)min((size_t)148 * 8, (rows + 7) / 8);
+  finish_apply_kernel<<<grid, 256, 0, st>>>(R, ln_g, ln_b, gn_g, gn_b, skip, stat, B, S, c, inter,
+                                            out, next_R, next_pe, next_ctok);
+  return check_launch("finish_apply_kernel");
+}
+
+// --------------------------------------------------------------------------------------------
+// pred_head[b,:] = mean over k of LN_final(R_inter[(b,k), 0, :])   (token 0 = first context row)
+// One CTA per sample; warp w folds rows k = w, w+8, ... in a fixed order (deterministic).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pred_head_kernel(const float* __restrict__ R,
+                                                        const float* __restrict__ ln_g,
+                                                        const float* __restrict__ ln_b, int S,
+                                                        int c, float* __restrict__ out) {
+  __shared__ float s_acc[8][kN];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const f8 gg = ld8(ln_g + lane * 8), bb = ld8(ln_b + lane * 8);
+  f8 acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+  for (int k = wid; k < kK; k += 8) {
+    f8 v = ld8(R + ((size_t)b * kK + k) * (size_t)(S + c) * kN + lane * 8);
+    ln_row(v, gg, bb, 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] += v.v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_acc[wid][lane * 8 + i] = acc.v[i];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
+  out[(size_t)b * kN + threadIdx.x] = t * (1.0f / kK);
+}
+
+int launch_pred_head(const float* R, const float* ln_g, const float* ln_b, int B, int S, int c,
+                     float* out, cudaStream_t st) {
+  pred_head_kernel<<<B, 256, 0, st>>>(R, ln_g, ln_b, S, c, out);
+  return check_launch("pred_head_kernel");
+}
+
+}  // namespace cse

@@ -1,0 +1,506 @@
+"""Host-side mirror of the reference's module API for the Sepformer hot path.
+
+Same class names, constructor arguments, parameter names/shapes and return conventions as
+`src/models/{ContSep,ContExt,sepformer,CSE_transformer}.py` and the speechbrain leaves they
+import, so `load_state_dict(ckpt['state_dict'])` and the train/test scripts work
+unchanged.  The modules own ordinary fp32 `nn.Parameter`s; every forward() launches the
+hand-written sm_100a kernels through the C ABI (`include/cse_b200.h`).  There is no PyTorch
+compute fallback: without the built library or on a CPU tensor the call raises.
+
+The kernels are specialised to the constants hard-coded in the reference constructors
+(ContSep.py:10-40): N=256, encoder k=16/s=8, K=250, 8 heads, d_ffn=1024, 8 layers, pre-norm,
+ReLU, dropout 0, norm='ln', no linear after intra/inter, skip around intra.
+"""
+import copy
+import ctypes as C
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import BF16, FP32
+from .runtime import WORKSPACE, ParamTable, current_stream, resolve_precision
+from .shapes import CHUNK, D_FFN, ENC_K, ENC_S, N_CH, N_HEAD, N_LAYER, PE_MAX
+
+EPS = 1e-8
+
+
+def _unsupported(what):
+    raise NotImplementedError(
+        f"{what}: the B200 kernels are specialised to the reference configuration "
+        "(N=256, kernel 16/stride 8, K=250, 8 heads, d_ffn=1024, 8 pre-norm ReLU layers, norm='ln')")
+
+
+def _act_dtype(precision):
+    return torch.bfloat16 if precision == BF16 else torch.float32
+
+
+def _check_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.CseError(f"{name} is on {t.device}: the CUDA path has no CPU fallback")
+
+
+_warned_grad = [False]
+
+
+def _warn_no_grad(module):
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()) and not _warned_grad[0]:
+        _warned_grad[0] = True
+        warnings.warn("cse_b200: forward kernels only so far — outputs carry no autograd graph")
+
+
+def select_norm(norm, dim, shape, eps=1e-8):
+    """speechbrain select_norm: 'ln' -> GroupNorm(1, dim, eps) (ContSep.py:164,423-424)."""
+    if norm == "ln":
+        return nn.GroupNorm(1, dim, eps=eps)
+    _unsupported(f"norm={norm!r}")
+
+
+# ----------------------------------------------------------------------------------------------
+# speechbrain leaves
+# ----------------------------------------------------------------------------------------------
+class Encoder(nn.Module):
+    """speechbrain Encoder (ContSep.py:10,69): relu(Conv1d(1,256,16,stride 8,bias=False)).
+    forward: [B,T] -> [B,256,L] (a transposed view of the channels-last kernel output)."""
+
+    def __init__(self, kernel_size=2, out_channels=64, in_channels=1):
+        super().__init__()
+        self.conv1d = nn.Conv1d(in_channels=in_channels, out_channels=out_channels,
+                                kernel_size=kernel_size, stride=kernel_size // 2, groups=1, bias=False)
+        self.in_channels = in_channels
+
+    def forward(self, x, precision=None):
+        w = self.conv1d.weight
+        if tuple(w.shape) != (N_CH, 1, ENC_K):
+            _unsupported(f"Encoder weight {tuple(w.shape)}")
+        if x.dim() != 2:
+            raise RuntimeError(f"Encoder expects [B,T], got {tuple(x.shape)}")
+        _check_cuda(x, "mix")
+        prec = resolve_precision(precision)
+        x = x.contiguous().float()
+        B, T = x.shape
+        sh = _lib.path_shape(B, T, 0, 1)
+        out = torch.empty(B, sh.L, N_CH, dtype=_act_dtype(prec), device=x.device)
+        part = torch.empty(B, (sh.L + 63) // 64, 2, dtype=torch.float32, device=x.device)
+        n_parts = C.c_int(0)
+        _lib.call("cse_encoder_fwd", _lib.ptr(x), _lib.ptr(w), B, T, prec, _lib.ptr(out), _lib.ptr(part),
+                  C.byref(n_parts), C.c_void_p(current_stream(x.device)))
+        return out.transpose(1, 2)
+
+
+class Decoder(nn.ConvTranspose1d):
+    """speechbrain Decoder (ContSep.py:40,84): ConvTranspose1d(256,1,16,stride=8,bias=False) whose
+    forward takes [B,N,L] and returns [B,T_est]."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x, precision=None):
+        if x.dim() not in [2, 3]:
+            raise RuntimeError("{} accept 3/4D tensor as input".format(type(self).__name__))
+        if tuple(self.weight.shape) != (N_CH, 1, ENC_K) or self.bias is not None or self.stride != (ENC_S,):
+            _unsupported(f"Decoder weight {tuple(self.weight.shape)}")
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        _check_cuda(x, "decoder input")
+        B, N, L = x.shape
+        rows = x.transpose(1, 2).contiguous().float()                # channels-last [B,L,N]
+        T_est = ENC_S * (L - 1) + ENC_K
+        frames = torch.empty(B * L, ENC_K, dtype=torch.float32, device=x.device)
+        est = torch.empty(B, T_est, 1, dtype=torch.float32, device=x.device)
+        _lib.call("cse_mask_decode", _lib.ptr(rows), None, _lib.ptr(self.weight), B, L, T_est, 1, FP32,
+                  _lib.ptr(frames), _lib.ptr(est), C.c_void_p(current_stream(x.device)))
+        return est.squeeze(-1)
+
+
+class PositionalEncoding(nn.Module):
+    """speechbrain PositionalEncoding (CSE_transformer.py:88): persistent sinusoid buffer `pe`."""
+
+    def __init__(self, input_size, max_len=PE_MAX):
+        super().__init__()
+        if input_size % 2 != 0:
+            raise ValueError(f"Cannot use sin/cos positional encoding with odd channels (got channels={input_size})")
+        self.max_len = max_len
+        pe = torch.zeros(max_len, input_size, requires_grad=False)
+        pos = torch.arange(0, max_len).unsqueeze(1).float()
+        freq = torch.exp(torch.arange(0, input_size, 2).float() * -(math.log(10000.0) / input_size))
+        pe[:, 0::2] = torch.sin(pos * freq)
+        pe[:, 1::2] = torch.cos(pos * freq)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):
+        return self.pe[:, : x.size(1)].clone().detach()
+
+
+class LayerNorm(nn.Module):
+    """sb.nnet.normalization.LayerNorm: parameter container `.norm` (CSE_transformer.py:197,358)."""
+
+    def __init__(self, input_size=None, input_shape=None, eps=1e-05, elementwise_affine=True):
+        super().__init__()
+        self.eps = eps
+        self.norm = nn.LayerNorm(input_size, eps=eps, elementwise_affine=elementwise_affine)
+
+
+class PositionalwiseFeedForward(nn.Module):
+    """sb.nnet.attention.PositionalwiseFeedForward: parameter container `.ffn.{0,3}`."""
+
+    def __init__(self, d_ffn, input_shape=None, input_size=None, dropout=0.0, activation=nn.ReLU):
+        super().__init__()
+        self.ffn = nn.Sequential(nn.Linear(input_size, d_ffn), activation(), nn.Dropout(dropout),
+                                 nn.Linear(d_ffn, input_size))
+
+
+# ----------------------------------------------------------------------------------------------
+# CSE_transformer.py mirror
+# ----------------------------------------------------------------------------------------------
+class MultiheadAttention(nn.Module):
+    """CSE_transformer.py:424-477: parameter container `.att` = nn.MultiheadAttention."""
+
+    def __init__(self, nhead, d_model, dropout=0.0, bias=True, add_bias_kv=False, add_zero_attn=False,
+                 kdim=None, vdim=None):
+        super().__init__()
+        self.att = nn.MultiheadAttention(embed_dim=d_model, num_heads=nhead, dropout=dropout, bias=bias,
+                                         add_bias_kv=add_bias_kv, add_zero_attn=add_zero_attn,
+                                         kdim=kdim, vdim=vdim)
+
+
+class TransformerEncoderLayer(nn.Module):
+    """CSE_transformer.py:253-364 (regularMHA + regularFFN, pre-norm)."""
+
+    def __init__(self, d_ffn, nhead, d_model, kdim=None, vdim=None, dropout=0.0, activation=nn.ReLU,
+                 normalize_before=False, attention_type="regularMHA", ffn_type="regularFFN",
+                 ffn_cnn_kernel_size_list=[3, 3], causal=False):
+        super().__init__()
+        if attention_type != "regularMHA" or ffn_type != "regularFFN" or causal:
+            _unsupported(f"attention_type={attention_type!r}, ffn_type={ffn_type!r}, causal={causal}")
+        self.self_att = MultiheadAttention(nhead=nhead, d_model=d_model, dropout=dropout, kdim=kdim, vdim=vdim)
+        self.pos_ffn = PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
+                                                 activation=activation)
+        self.norm1 = LayerNorm(d_model, eps=1e-6)
+        self.norm2 = LayerNorm(d_model, eps=1e-6)
+        self.dropout1 = torch.nn.Dropout(dropout)
+        self.dropout2 = torch.nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+        self.pos_ffn_type = ffn_type
+
+
+class TransformerEncoder(nn.Module):
+    """CSE_transformer.py:109-199: `layers` + final `norm` (eps 1e-6)."""
+
+    def __init__(self, num_layers, nhead, d_ffn, input_shape=None, d_model=None, kdim=None, vdim=None,
+                 dropout=0.0, activation=nn.ReLU, normalize_before=False, causal=False,
+                 layerdrop_prob=0.0, attention_type="regularMHA", ffn_type="regularFFN",
+                 ffn_cnn_kernel_size_list=[3, 3]):
+        super().__init__()
+        self.layers = torch.nn.ModuleList([
+            TransformerEncoderLayer(d_ffn=d_ffn, nhead=nhead, d_model=d_model, kdim=kdim, vdim=vdim,
+                                    dropout=dropout, activation=activation,
+                                    normalize_before=normalize_before, causal=causal,
+                                    attention_type=attention_type, ffn_type=ffn_type,
+                                    ffn_cnn_kernel_size_list=ffn_cnn_kernel_size_list)
+            for _ in range(num_layers)])
+        self.norm = LayerNorm(d_model, eps=1e-6)
+        self.layerdrop_prob = layerdrop_prob
+
+
+class SBTransformerBlock_CSE(nn.Module):
+    """CSE_transformer.py:11-106.  forward: [B',n,256] -> [B',n,256] = LN(8 layers(x + pe[:n]))."""
+
+    def __init__(self, num_layers, d_model, nhead, d_ffn=2048, input_shape=None, kdim=None, vdim=None,
+                 dropout=0.1, activation="relu", use_positional_encoding=False, norm_before=False,
+                 attention_type="regularMHA"):
+        super().__init__()
+        self.use_positional_encoding = use_positional_encoding
+        if activation == "relu":
+            act = nn.ReLU
+        elif activation == "gelu":
+            act = nn.GELU
+        else:
+            raise ValueError("unknown activation")
+        self._cfg = dict(num_layers=num_layers, d_model=d_model, nhead=nhead, d_ffn=d_ffn, dropout=dropout,
+                         activation=activation, norm_before=norm_before, pe=use_positional_encoding)
+        self.mdl = TransformerEncoder(num_layers=num_layers, nhead=nhead, d_ffn=d_ffn, input_shape=input_shape,
+                                      d_model=d_model, kdim=kdim, vdim=vdim, dropout=dropout, activation=act,
+                                      normalize_before=norm_before, attention_type=attention_type)
+        if use_positional_encoding:
+            self.pos_enc = PositionalEncoding(input_size=d_model)
+        self._w16 = {}
+
+    def _check_supported(self):
+        c = self._cfg
+        ok = (c["num_layers"] == N_LAYER and c["d_model"] == N_CH and c["nhead"] == N_HEAD
+              and c["d_ffn"] == D_FFN and c["activation"] == "relu" and c["norm_before"] and c["pe"]
+              and (c["dropout"] == 0 or not self.training))
+        if not ok:
+            _unsupported(f"SBTransformerBlock_CSE{c}")
+
+    def _weight(self, w, prec):
+        if prec == FP32:
+            return w
+        key = id(w)
+        ent = self._w16.get(key)
+        if ent is None or ent[0] != (w.data_ptr(), w._version):
+            ent = ((w.data_ptr(), w._version), w.detach().to(torch.bfloat16).contiguous())
+            self._w16[key] = ent
+        return ent[1]
+
+    def forward(self, x, precision=None):
+        """Stand-alone block through the per-stage C-ABI entry points (the fused model path runs the
+        same kernels from cse_forward)."""
+        self._check_supported()
+        _check_cuda(x, "x")
+        prec = resolve_precision(precision)
+        Bp, n, E = x.shape
+        if E != N_CH:
+            _unsupported(f"d_model={E}")
+        st = C.c_void_p(current_stream(x.device))
+        dev, adt = x.device, _act_dtype(prec)
+        R = (x.float() + self.pos_enc.pe[:, :n]).contiguous()          # residual stream, fp32
+        M = Bp * n
+        H = torch.empty(M, N_CH, dtype=adt, device=dev)
+        QKV = torch.empty(M, 3 * N_CH, dtype=adt, device=dev)
+        AO = torch.empty(M, N_CH, dtype=adt, device=dev)
+        F1 = torch.empty(M, D_FFN, dtype=adt, device=dev)
+        for layer in self.mdl.layers:
+            att, ffn = layer.self_att.att, layer.pos_ffn.ffn
+            _lib.call("cse_layernorm_fwd", _lib.ptr(R), _lib.ptr(layer.norm1.norm.weight),
+                      _lib.ptr(layer.norm1.norm.bias), M, 1e-6, prec, _lib.ptr(H), st)
+            _lib.call("cse_linear", _lib.ptr(H), N_CH, _lib.ptr(self._weight(att.in_proj_weight, prec)),
+                      _lib.ptr(att.in_proj_bias), 1.0, None, _lib.ptr(QKV), 3 * N_CH, M, 3 * N_CH, N_CH, 0, 0,
+                      prec, st)
+            _lib.call("cse_attention_fwd", _lib.ptr(QKV), Bp, n, prec, _lib.ptr(AO), st)
+            _lib.call("cse_linear", _lib.ptr(AO), N_CH, _lib.ptr(self._weight(att.out_proj.weight, prec)),
+                      _lib.ptr(att.out_proj.bias), 1.0, _lib.ptr(R), _lib.ptr(R), N_CH, M, N_CH, N_CH, 0, 1,
+                      prec, st)
+            _lib.call("cse_layernorm_fwd", _lib.ptr(R), _lib.ptr(layer.norm2.norm.weight),
+                      _lib.ptr(layer.norm2.norm.bias), M, 1e-6, prec, _lib.ptr(H), st)
+            _lib.call("cse_linear", _lib.ptr(H), N_CH, _lib.ptr(self._weight(ffn[0].weight, prec)),
+                      _lib.ptr(ffn[0].bias), 1.0, None, _lib.ptr(F1), D_FFN, M, D_FFN, N_CH, 1, 0, prec, st)
+            _lib.call("cse_linear", _lib.ptr(F1), D_FFN, _lib.ptr(self._weight(ffn[3].weight, prec)),
+                      _lib.ptr(ffn[3].bias), 1.0, _lib.ptr(R), _lib.ptr(R), N_CH, M, N_CH, D_FFN, 0, 1, prec, st)
+        out = torch.empty(Bp, n, N_CH, dtype=torch.float32, device=dev)
+        _lib.call("cse_layernorm_fwd", _lib.ptr(R), _lib.ptr(self.mdl.norm.norm.weight),
+                  _lib.ptr(self.mdl.norm.norm.bias), M, 1e-6, FP32, _lib.ptr(out), st)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# dual-path model
+# ----------------------------------------------------------------------------------------------
+class Dual_Computation_Block_CSE(nn.Module):
+    """ContSep.py:372-533 / ContExt.py:398-557: parameter container for one dual-path block
+    (intra_mdl, inter_mdl, intra_norm, inter_norm, optional context mappers)."""
+
+    def __init__(self, intra_mdl, inter_mdl, out_channels, norm="ln", skip_around_intra=True,
+                 linear_layer_after_inter_intra=True, llm_dim=4096):
+        super().__init__()
+        if linear_layer_after_inter_intra or not skip_around_intra or norm != "ln":
+            _unsupported("Dual_Computation_Block with linear_layer_after_inter_intra / no skip / norm != 'ln'")
+        self.intra_mdl = intra_mdl
+        self.inter_mdl = inter_mdl
+        self.skip_around_intra = skip_around_intra
+        self.linear_layer_after_inter_intra = linear_layer_after_inter_intra
+        self.llm_dim = llm_dim
+        self.out_channels = out_channels
+        self.norm = norm
+        self.intra_norm = select_norm(norm, out_channels, 4)
+        self.inter_norm = select_norm(norm, out_channels, 4)
+        self.intra_context_mapper = None
+        self.inter_context_mapper = None
+
+    def add_ctx(self):
+        self.intra_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
+        self.inter_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
+
+
+class Dual_Path_Model_CSE(nn.Module):
+    """ContSep.py:103-370.  forward(x [B,N,L], ctx [B,c,4096] | None) ->
+    (mask [spk,B,N,L], pred_head [B,N]) in the ContSep flavour, mask alone in the ContExt /
+    speechbrain flavours (`returns_pred_head`)."""
+
+    returns_pred_head = True
+
+    def __init__(self, in_channels, out_channels, intra_model, inter_model, num_layers=1, norm="ln", K=200,
+                 num_spks=2, skip_around_intra=True, linear_layer_after_inter_intra=True,
+                 use_global_pos_enc=False, max_length=20000, llm_dim=4096):
+        super().__init__()
+        if use_global_pos_enc:
+            _unsupported("use_global_pos_enc=True")
+        self.K = K
+        self.num_spks = num_spks
+        self.num_layers = num_layers
+        self.norm = select_norm(norm, in_channels, 3)
+        self.conv1d = nn.Conv1d(in_channels, out_channels, 1, bias=False)
+        self.use_global_pos_enc = use_global_pos_enc
+        self.dual_mdl = nn.ModuleList([])
+        for _ in range(num_layers):
+            self.dual_mdl.append(copy.deepcopy(Dual_Computation_Block_CSE(
+                intra_model, inter_model, out_channels, norm, skip_around_intra=skip_around_intra,
+                linear_layer_after_inter_intra=linear_layer_after_inter_intra, llm_dim=llm_dim)))
+        self.conv2d = nn.Conv2d(out_channels, out_channels * num_spks, kernel_size=1)
+        self.end_conv1x1 = nn.Conv1d(out_channels, in_channels, 1, bias=False)
+        self.prelu = nn.PReLU()
+        self.activation = nn.ReLU()
+        self.output = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Tanh())
+        self.output_gate = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Sigmoid())
+        self._table = ParamTable()
+
+    def add_ctx(self):
+        for i in range(self.num_layers):
+            self.dual_mdl[i].add_ctx()
+
+    def _check_supported(self):
+        if self.K != CHUNK or self.num_layers != 2 or self.conv1d.weight.shape[0] != N_CH:
+            _unsupported(f"Dual_Path_Model(K={self.K}, num_layers={self.num_layers})")
+        for blk in self.dual_mdl:
+            blk.intra_mdl._check_supported()
+            blk.inter_mdl._check_supported()
+
+    def _tensors(self, prefix="masknet."):
+        out = {prefix + k: v for k, v in self.named_parameters()}
+        out.update({prefix + k: v for k, v in self.named_buffers()})
+        return out
+
+    def forward(self, x, ctx=None, precision=None):
+        self._check_supported()
+        _check_cuda(x, "x")
+        _warn_no_grad(self)
+        prec = resolve_precision(precision)
+        B, N, L = x.shape
+        c = 0 if ctx is None else ctx.size(1)
+        dev = x.device
+        stream = current_stream(dev)
+        tensors = self._tensors()
+        # the stand-alone masknet never touches encoder/decoder weights; give the table placeholders
+        tensors["encoder.conv1d.weight"] = self.conv1d.weight
+        tensors["decoder.weight"] = self.conv1d.weight
+        params = self._table.build(tensors, self.num_spks, prec, stream)
+        E = x.transpose(1, 2).to(_act_dtype(prec)).contiguous()
+        lib = _lib.load()
+        T_equiv = ENC_S * (L - 1) + ENC_K
+        nbytes = lib.cse_workspace_bytes(B, T_equiv, c, self.num_spks, prec)
+        if nbytes == 0:
+            raise _lib.CseError(lib.cse_last_error().decode())
+        keep, ws_ptr, ws_len = WORKSPACE.get(nbytes, dev)
+        mask = torch.empty(B, L, self.num_spks, N_CH, dtype=torch.float32, device=dev)
+        pred = torch.empty(B, N_CH, dtype=torch.float32, device=dev)
+        ctx_d = None if ctx is None else ctx.contiguous().float()
+        _lib.call("cse_masknet_fwd", C.byref(params), _lib.ptr(E), _lib.ptr(ctx_d), B, L, c, self.num_spks, prec,
+                  _lib.ptr(mask), _lib.ptr(pred), C.c_void_p(ws_ptr), ws_len, C.c_void_p(stream))
+        mask = mask.permute(2, 0, 3, 1)                     # [spk,B,N,L] view
+        if self.returns_pred_head:
+            return mask, pred
+        return mask
+
+
+class Dual_Path_Model(Dual_Path_Model_CSE):
+    """speechbrain Dual_Path_Model (sepformer.py:11): no context, forward(x) -> mask."""
+
+    returns_pred_head = False
+
+    def __init__(self, in_channels, out_channels, intra_model, inter_model, num_layers=1, norm="ln", K=200,
+                 num_spks=2, skip_around_intra=True, linear_layer_after_inter_intra=True,
+                 use_global_pos_enc=False, max_length=20000):
+        super().__init__(in_channels, out_channels, intra_model, inter_model, num_layers=num_layers,
+                         norm=norm, K=K, num_spks=num_spks, skip_around_intra=skip_around_intra,
+                         linear_layer_after_inter_intra=linear_layer_after_inter_intra,
+                         use_global_pos_enc=use_global_pos_enc, max_length=max_length, llm_dim=None)
+
+    def forward(self, x, precision=None):
+        return super().forward(x, None, precision=precision)
+
+
+class Dual_Path_Model_CSE_Ext(Dual_Path_Model_CSE):
+    """ContExt.py:132-294 flavour: forward returns the mask only."""
+
+    returns_pred_head = False
+
+
+# ----------------------------------------------------------------------------------------------
+# fused top-level path shared by the three Sepformer flavours
+# ----------------------------------------------------------------------------------------------
+def _make_masknet(cls, num_spks, **extra):
+    def block():
+        return SBTransformerBlock_CSE(num_layers=8, d_model=256, nhead=8, d_ffn=1024, dropout=0,
+                                      use_positional_encoding=True, norm_before=True)
+    return cls(num_spks=num_spks, in_channels=256, out_channels=256, num_layers=2, K=250,
+               intra_model=block(), inter_model=block(), norm="ln",
+               linear_layer_after_inter_intra=False, skip_around_intra=True, **extra)
+
+
+class _SepformerBase(nn.Module):
+    """encoder -> masknet(ctx) -> mask * mix_w -> decoder -> pad/trim as ONE C-ABI call."""
+
+    precision = None        # None: follow torch.autocast; or 'fp32' / 'bf16'
+
+    def _init_common(self):
+        self._table = ParamTable()
+
+    def _tensors(self):
+        out = {}
+        for prefix, mod in (("encoder.", self.encoder), ("masknet.", self.masknet), ("decoder.", self.decoder)):
+            for k, v in mod.named_parameters():
+                out[prefix + k] = v
+            for k, v in mod.named_buffers():
+                out[prefix + k] = v
+        return out
+
+    def _run(self, mix, ctx, n_masks, want_pred_head):
+        """mix [B,T], ctx [B,c,4096] | None -> est [B,T,n_masks] fp32 (+ pred_head [B,256])."""
+        self.masknet._check_supported()
+        if mix.dim() != 2:
+            raise RuntimeError(f"mix must be [B,T], got {tuple(mix.shape)}")
+        _check_cuda(mix, "mix")
+        _warn_no_grad(self)
+        prec = resolve_precision(self.precision)
+        dev = mix.device
+        stream = current_stream(dev)
+        mix = mix.contiguous().float()
+        B, T = mix.shape
+        c = 0
+        if ctx is not None:
+            if ctx.dim() != 3 or ctx.size(0) != B or ctx.size(2) != self.masknet.dual_mdl[0].llm_dim:
+                raise RuntimeError(f"ctx must be [B,c,{self.masknet.dual_mdl[0].llm_dim}], got {tuple(ctx.shape)}")
+            ctx = ctx.contiguous().float()
+            c = ctx.size(1)
+        params = self._table.build(self._tensors(), n_masks, prec, stream)
+        lib = _lib.load()
+        nbytes = lib.cse_workspace_bytes(B, T, c, n_masks, prec)
+        if nbytes == 0:
+            raise _lib.CseError(lib.cse_last_error().decode())
+        keep, ws_ptr, ws_len = WORKSPACE.get(nbytes, dev)
+        est = torch.empty(B, T, n_masks, dtype=torch.float32, device=dev)
+        pred = torch.empty(B, N_CH, dtype=torch.float32, device=dev) if want_pred_head else None
+        _lib.call("cse_forward", C.byref(params), _lib.ptr(mix), _lib.ptr(ctx), B, T, c, n_masks, prec,
+                  _lib.ptr(est), _lib.ptr(pred), C.c_void_p(ws_ptr), ws_len, C.c_void_p(stream))
+        return est, pred
+
+    def separate_host(self, mix_host, ctx_host=None, n_masks=None, est_host=None):
+        """End-to-end entry with HOST (pinned) buffers through cse_forward_host: H2D, forward, D2H.
+        Returns est_host [B,T,n_masks] (and pred_head_host for the ContSep flavour)."""
+        prec = resolve_precision(self.precision)
+        dev = next(self.parameters()).device
+        stream = current_stream(dev)
+        B, T = mix_host.shape
+        c = 0 if ctx_host is None else ctx_host.size(1)
+        n_masks = n_masks or self._n_masks()
+        params = self._table.build(self._tensors(), n_masks, prec, stream)
+        lib = _lib.load()
+        nbytes = lib.cse_workspace_bytes(B, T, c, n_masks, prec)
+        if nbytes == 0:
+            raise _lib.CseError(lib.cse_last_error().decode())
+        keep, ws_ptr, ws_len = WORKSPACE.get(nbytes, dev)
+        if est_host is None:
+            est_host = torch.empty(B, T, n_masks, dtype=torch.float32).pin_memory()
+        pred_host = torch.empty(B, N_CH, dtype=torch.float32).pin_memory() if self._wants_pred() else None
+        _lib.call("cse_forward_host", C.byref(params), _lib.ptr(mix_host), _lib.ptr(ctx_host), B, T, c, n_masks,
+                  prec, _lib.ptr(est_host), _lib.ptr(pred_host), C.c_void_p(ws_ptr), ws_len, C.c_void_p(stream))
+        return est_host, pred_host
+
+    def _n_masks(self):
+        return self.num_spks
+
+    def _wants_pred(self):
+        return False

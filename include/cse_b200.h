@@ -1,0 +1,255 @@
+/* cse_b200.h — C ABI of the B200-native Sepformer hot path.
+ *
+ * The reference (miraodasilva/contextual-speech-extraction) is pure Python and exposes no FFI;
+ * its seam for this path is Python class composition.  This header is the
+ * boundary a maintainer would bind instead: plain pointers and sizes, caller-owned DEVICE
+ * memory, no hidden allocation, kernels launched on the caller's stream.  Each entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; cse_last_error() gives the text
+ *     (thread-local).  Nothing aborts the process.
+ *   - all pointers are device pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - activations are CHANNELS-LAST: a [B,N,L] reference tensor is stored [B,L,N] (N = 256).
+ *   - `precision`: CSE_FP32 = true-fp32 arithmetic (parity mode, <=1e-4 rel-L2 vs the fp32
+ *     reference); CSE_BF16 = bf16 tensor-core operands, fp32 accumulate / residual / norms
+ *     (the reference's autocast policy; performance mode).
+ */
+#ifndef CSE_B200_H
+#define CSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSE_API __attribute__((visibility("default")))
+
+#define CSE_FP32 0
+#define CSE_BF16 1
+
+#define CSE_N 256        /* channels            ContSep.py:10,13-14 */
+#define CSE_K 250        /* chunk length        ContSep.py:16       */
+#define CSE_LAYERS 8     /* layers per stack    ContSep.py:18       */
+#define CSE_BLOCKS 2     /* dual-path blocks    ContSep.py:15       */
+#define CSE_FFN 1024     /* FFN width           ContSep.py:21       */
+#define CSE_HEADS 8      /* attention heads     ContSep.py:20       */
+#define CSE_CTX 4096     /* context width       ContSep.py:8        */
+
+/* One pre-norm transformer layer (CSE_transformer.py:253-421).  fp32 master pointers are the
+ * nn.Parameter storages; *_bf16 are the packed copies written by cse_pack_bf16 (CSE_BF16 only). */
+typedef struct {
+  const float* in_proj_w;   /* [768,256]  self_att.att.in_proj_weight */
+  const float* in_proj_b;   /* [768] */
+  const float* out_proj_w;  /* [256,256]  self_att.att.out_proj.weight */
+  const float* out_proj_b;  /* [256] */
+  const float* ffn1_w;      /* [1024,256] pos_ffn.ffn.0.weight */
+  const float* ffn1_b;      /* [1024] */
+  const float* ffn2_w;      /* [256,1024] pos_ffn.ffn.3.weight */
+  const float* ffn2_b;      /* [256] */
+  const float* ln1_g;       /* norm1.norm.weight */
+  const float* ln1_b;
+  const float* ln2_g;       /* norm2.norm.weight */
+  const float* ln2_b;
+  const void* in_proj_w_bf16;
+  const void* out_proj_w_bf16;
+  const void* ffn1_w_bf16;
+  const void* ffn2_w_bf16;
+} cse_layer_params;
+
+/* SBTransformerBlock_CSE (CSE_transformer.py:11-106): 8 layers + final LayerNorm + PE table. */
+typedef struct {
+  cse_layer_params layer[CSE_LAYERS];
+  const float* final_g;     /* mdl.norm.norm.weight */
+  const float* final_b;
+  const float* pe;          /* pos_enc.pe [2500,256] */
+} cse_stack_params;
+
+/* Dual_Computation_Block_CSE (ContSep.py:372-533). */
+typedef struct {
+  cse_stack_params intra;
+  cse_stack_params inter;
+  const float* intra_norm_g;  /* GroupNorm(1,256) affine */
+  const float* intra_norm_b;
+  const float* inter_norm_g;
+  const float* inter_norm_b;
+  const float* intra_map_w;   /* intra_context_mapper.weight [256,4096] or NULL (c == 0) */
+  const float* intra_map_b;
+  const float* inter_map_w;
+  const float* inter_map_b;
+} cse_block_params;
+
+/* Encoder + Dual_Path_Model_CSE + Decoder (ContSep.py:7-100, 103-370). */
+typedef struct {
+  const float* enc_w;       /* encoder.conv1d.weight [256,16] */
+  const float* norm_g;      /* masknet.norm */
+  const float* norm_b;
+  const float* conv1d_w;    /* masknet.conv1d.weight [256,256] */
+  cse_block_params block[CSE_BLOCKS];
+  const float* prelu;       /* masknet.prelu.weight [1] */
+  const float* conv2d_w;    /* masknet.conv2d.weight [spk*256,256] */
+  const float* conv2d_b;    /* [spk*256] */
+  const float* out_w;       /* masknet.output.0 [256,256] */
+  const float* out_b;
+  const float* gate_w;      /* masknet.output_gate.0 */
+  const float* gate_b;
+  const float* end_w;       /* masknet.end_conv1x1.weight [256,256] */
+  const float* dec_w;       /* decoder.weight [256,16] */
+  const void* conv1d_w_bf16;
+  const void* conv2d_w_bf16;
+  const void* out_w_bf16;
+  const void* gate_w_bf16;
+  const void* end_w_bf16;
+} cse_params;
+
+/* ---- library ---- */
+CSE_API int cse_version(void);
+CSE_API const char* cse_last_error(void);
+
+/* ---- shape algebra (ContSep.py:270-335 `_padding/_Segmentation`; encoder/decoder lengths) ---- */
+typedef struct {
+  int B, T, c, spk;
+  int L;      /* encoder frames (T-16)/8+1 */
+  int gap;    /* ContSep.py:287 */
+  int S;      /* chunks */
+  int T_est;  /* 8(L-1)+16 */
+} cse_shape;
+CSE_API int cse_path_shape(int B, int T, int c, int spk, cse_shape* out);
+
+/* ---- whole path ---- */
+/* Bytes of scratch cse_forward needs for this call (caller allocates, 256-byte aligned). */
+CSE_API size_t cse_workspace_bytes(int B, int T, int c, int n_masks, int precision);
+
+/* Number of bf16 elements cse_pack_bf16 writes; then fills the *_bf16 members of `p`
+ * (host struct) with pointers into `packed`.  Replaces autocast's per-call weight casts. */
+CSE_API size_t cse_pack_bf16_elems(int n_masks);
+CSE_API int cse_pack_bf16(cse_params* p_host, int n_masks, void* packed, size_t packed_elems,
+                          void* stream);
+
+/* Sepformer.forward minus the two host-side Linear layers (ContSep.py:53-100, ContExt.py:54-129,
+ * sepformer.py:42-81): encoder -> masknet(ctx) -> mask * mix_w -> decoder -> pad/trim.
+ *   mix  [B,T] fp32;  ctx [B,c,4096] fp32 or NULL when c == 0
+ *   n_masks: masks to estimate AND decode (spk for Sepformer/ContSep; 1 for ContExt, which uses
+ *            only est_mask[0], ContExt.py:113-119 — conv2d rows [0,256) suffice)
+ *   est  [B,T,n_masks] fp32 out
+ *   pred_head [B,256] fp32 out or NULL (ContSep.py:516-517, last block's inter token 0 mean) */
+CSE_API int cse_forward(const cse_params* p_host, const float* mix, const float* ctx,
+                        int B, int T, int c, int n_masks, int precision,
+                        float* est, float* pred_head,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned recommended): H2D of mix/ctx, forward, D2H of est and
+ * pred_head, stream-ordered; returns after the stream is synchronised.  The reference-facing
+ * end-to-end entry (`model(mix.cuda(), ctx).cpu()` in test.py:231-245). */
+CSE_API int cse_forward_host(const cse_params* p_host, const float* mix_host, const float* ctx_host,
+                             int B, int T, int c, int n_masks, int precision,
+                             float* est_host, float* pred_head_host,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dual_Path_Model_CSE.forward on its own (ContSep.py:205-268; speechbrain Dual_Path_Model when
+ * c == 0): E = mix_w channels-last [B,L,256] in the activation dtype of `precision` ->
+ * mask [B,L,n_masks,256] fp32 (post-ReLU; reference layout mask[s,b,n,l]) and pred_head. */
+CSE_API int cse_masknet_fwd(const cse_params* p_host, const void* E, const float* ctx,
+                            int B, int L, int c, int n_masks, int precision,
+                            float* mask, float* pred_head,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- per-stage entry points (unit-testable; same kernels cse_forward launches) ---- */
+/* act_dtype: CSE_FP32 -> float activations, CSE_BF16 -> __nv_bfloat16 activations. */
+
+/* speechbrain Encoder: relu(conv1d(k=16,s=8,no bias)) (ContSep.py:10,69).  mix [B,T] ->
+ * out [B,L,256] act; also per-CTA (sum,sumsq) partials for masknet.norm -> gn_part [B,parts,2]. */
+CSE_API int cse_encoder_fwd(const float* mix, const float* w, int B, int T, int act_dtype,
+                            void* out, float* gn_part, int* n_parts, void* stream);
+
+/* GroupNorm(1,256,eps=1e-8) statistics finalise: partials -> (mean, rstd) [B,2] (ContSep.py:164). */
+CSE_API int cse_gn_finalize(const float* gn_part, int B, int n_parts, double count, float eps,
+                            float* stat, void* stream);
+
+/* masknet.norm apply (ContSep.py:226): out = (x-mean)*rstd*g + b, x [B,L,256] act -> act. */
+CSE_API int cse_gn_apply(const void* x, const float* stat, const float* g, const float* b,
+                         int B, int L, int act_dtype, void* out, void* stream);
+
+/* nn.Linear / 1x1 conv: C[M,N] = A[M,K] W[N,K]^T (+bias)(relu)(+residual).
+ * CSE_FP32: fp32 SIMT FFMA.  CSE_BF16: tcgen05 + TMA, bf16 operands (W must be bf16), fp32
+ * accumulate in TMEM.  out_fp32 != 0 -> C is float (residual, if given, is float [M,N] and
+ * may alias C); else C has the activation dtype.  bias_scale multiplies the bias (2 for the
+ * overlap-add / conv2d commutation). */
+CSE_API int cse_linear(const void* A, int lda, const void* W, const float* bias, float bias_scale,
+                       const float* residual, void* C, int ldc, int M, int N, int K,
+                       int relu, int out_fp32, int precision, void* stream);
+
+/* nn.LayerNorm(256, eps) over rows (CSE_transformer.py:358-359,386,408): x [M,256] fp32 -> act. */
+CSE_API int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps,
+                              int act_dtype, void* out, void* stream);
+
+/* nn.MultiheadAttention core (CSE_transformer.py:535-557 -> F.sdpa): qkv [nseq*n,768] act with
+ * q|k|v column blocks, 8 heads of 32 -> out [nseq*n,256] act.  No mask, no dropout. */
+CSE_API int cse_attention_fwd(const void* qkv, int nseq, int n, int act_dtype, void* out,
+                              void* stream);
+
+/* _padding + _Segmentation (ContSep.py:270-335): x0 [B,L,256] fp32 -> X [B,S,K,256] fp32. */
+CSE_API int cse_segment(const float* x0, int B, int L, int S, float* X, void* stream);
+
+/* Context-token prompt + positional encoding (ContSep.py:474-482 / :506-513 and
+ * CSE_transformer.py:102-104): builds the residual stream of a stack.
+ *   inter == 0: R[(b*S+s), c+k, :] = X[b,s,k,:] + pe[c+k];  inter != 0: R[(b*K+k), c+s, :] = ...
+ *   rows j < c: ctok[b,j,:] + pe[j].  X [B,S,K,256] fp32, ctok [B,c,256] fp32 or NULL. */
+CSE_API int cse_build_sequences(const float* X, const float* ctok, const float* pe,
+                                int B, int S, int c, int inter, float* R, void* stream);
+
+/* {intra,inter}_context_mapper = nn.Linear(4096,256) (ContSep.py:450-451,480,511). */
+CSE_API int cse_context_map(const float* ctx, const float* w, const float* b, int rows, int in_dim,
+                            float* out, void* stream);
+
+/* Tail of a stack inside Dual_Computation_Block_CSE.forward (ContSep.py:487-502 / :518-531):
+ * final LayerNorm(eps 1e-6) of R, drop the c context rows, GroupNorm(1,256,eps 1e-8) over the
+ * sample, + skip.  out [B,S,K,256] fp32.  skip [B,S,K,256] fp32.  Uses scratch gn_part/stat. */
+CSE_API int cse_stack_finish(const float* R, const float* ln_g, const float* ln_b,
+                             const float* gn_g, const float* gn_b, const float* skip,
+                             int B, int S, int c, int inter, float* out,
+                             float* gn_part, float* stat, void* stream);
+
+/* pred_head = mean_k LN(R_inter[(b,k), 0, :]) (ContSep.py:516-517). */
+CSE_API int cse_pred_head(const float* R_inter, const float* ln_g, const float* ln_b,
+                          int B, int S, int c, float* pred_head, void* stream);
+
+/* PReLU then _over_add (ContSep.py:244,337-370), commuted in front of conv2d:
+ * X [B,S,K,256] fp32 -> U [B,L,256] act. */
+CSE_API int cse_prelu_overlap_add(const float* X, const float* prelu, int B, int S, int L,
+                                  int act_dtype, void* U, void* stream);
+
+/* tanh(o) * sigmoid(g) (ContSep.py:255). */
+CSE_API int cse_gate(const void* o, const void* g, size_t n, int act_dtype, void* out, void* stream);
+
+/* ReLU mask, mask*mix_w, ConvTranspose1d(256,1,16,stride 8) and length fix
+ * (ContSep.py:263,79-95): mask_pre [B*L*n_masks,256] act (row = (b,l,s)), E [B,L,256] act,
+ * dec_w [256,16] -> est [B,T,n_masks] fp32.  frames scratch [B*L*n_masks,16] fp32. */
+/* E == NULL: plain Decoder.forward on an already-masked [rows,256] input (no ReLU/multiply). */
+CSE_API int cse_mask_decode(const void* mask_pre, const void* E, const float* dec_w,
+                            int B, int L, int T, int n_masks, int act_dtype,
+                            float* frames, float* est, void* stream);
+
+/* ---- losses ---- */
+/* speechbrain cal_si_snr (train_ContSep.py:352,386): NEGATIVE SI-SNR of `estimate` against
+ * `source`; both [B,T,C] fp32 (batch-major; the reference passes [T,B,C]) -> out [B,C]. */
+CSE_API int cse_si_snr(const float* source, const float* estimate, int B, int T, int C,
+                       float* out, void* stream);
+
+/* get_si_snr_with_pitwrapper(source, estimate_source) (train_ContSep.py:346,391-393):
+ * [B,T,C] x2 -> loss [B], perm [B,C] (perm[b,i] = column of `source` paired with
+ * estimate_source[:, :, i]).  C <= 4. */
+CSE_API int cse_pit_si_snr(const float* source, const float* estimate_source, int B, int T, int C,
+                           float* loss, int* perm, void* stream);
+
+/* torchmetrics ScaleInvariantSignalNoiseRatio (train_ContExt.py:339,367): [B,T] x2 -> dB [B]. */
+CSE_API int cse_tm_si_snr(const float* preds, const float* target, int B, int T,
+                          float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSE_B200_H */

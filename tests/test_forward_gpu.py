@@ -1,0 +1,162 @@
+"""GPU: the whole path through the module API / C ABI against the committed golden vectors
+(reference modules' own outputs) and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4 relative L2 on separated waveforms;
+bf16 mode within 0.05 dB SI-SNR of the reference output."""
+import pytest
+import torch
+
+import cse_b200  # noqa: F401
+from cse_b200 import synth
+from cse_b200.models.ContExt import Sepformer as ContExt
+from cse_b200.models.ContSep import Sepformer as ContSep
+from cse_b200.models.sepformer import Sepformer as PlainSepformer
+from helpers import MODEL_CASES, load_golden, model_case, rel_l2
+from oracle import sepformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+FP32_TOL = 1e-4          # relative L2, fp32 mode
+BF16_SISNR_TOL_DB = 0.05  # |SI-SNR(ours, src) - SI-SNR(reference, src)|
+BF16_REL_TOL = 3e-2      # sanity bound on the bf16 waveform error itself
+
+
+def build_model(meta):
+    v, spk = meta["variant"], meta["spk"]
+    if v == "sepformer":
+        m = PlainSepformer(spk)
+    elif v == "contsep":
+        m = ContSep(spk, add_mt=True, ce=meta["ce"])
+        m.add_mt_pipeline()
+    elif v == "context":
+        m = ContExt(spk, add_ctx=True)
+        m.add_ctx_pipeline()
+    else:
+        m = ContExt(spk, add_ctx=True, add_se=True)
+        m.add_ctx_pipeline()
+        m.add_se_pipeline()
+    return m
+
+
+def run_model(m, meta, mix, ctx, se):
+    mix = mix.to(DEV)
+    ctx = None if ctx is None else ctx.to(DEV)
+    with torch.no_grad():
+        if meta["variant"] == "sepformer":
+            out = m(mix)
+        elif meta["variant"] == "hcontext":
+            out = m(mix, ctx, se.to(DEV), cue=meta["cue"])
+        else:
+            out = m(mix, ctx)
+    torch.cuda.synchronize()
+    return out if isinstance(out, tuple) else (out, None)
+
+
+def si_snr_db(est, src):
+    """dB SI-SNR of every estimated stream against every source (zero-mean), [B,C_est,C_src]."""
+    e = est.double() - est.double().mean(1, keepdim=True)
+    s = src.double() - src.double().mean(1, keepdim=True)
+    dot = torch.einsum("bte,bts->bes", e, s)
+    s_en = (s * s).sum(1).unsqueeze(1) + 1e-12
+    proj_en = dot * dot / s_en
+    noise_en = (e * e).sum(1).unsqueeze(2) - proj_en
+    return 10 * torch.log10(proj_en / noise_en.clamp_min(1e-30) + 1e-30)
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_forward_fp32_matches_reference_golden(name):
+    sd, mix, src, ctx, se, meta = model_case(name)
+    m = build_model(meta)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    m.precision = "fp32"
+    est, pred = run_model(m, meta, mix, ctx, se)
+    gold = load_golden(name)
+    assert est.shape == gold["est"].shape
+    assert rel_l2(est.cpu(), gold["est"]) < FP32_TOL
+    if "context_pred" in gold:
+        assert pred.shape == gold["context_pred"].shape
+        assert rel_l2(pred.cpu(), gold["context_pred"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", [n for n in MODEL_CASES if MODEL_CASES[n][5] >= 1000])
+def test_forward_bf16_within_si_snr_tolerance(name):
+    sd, mix, src, ctx, se, meta = model_case(name)
+    m = build_model(meta)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16):        # the reference's --bf16 switch
+        est, pred = run_model(m, meta, mix, ctx, se)
+    gold = load_golden(name)["est"]
+    assert est.shape == gold.shape and est.dtype == torch.float32
+    assert rel_l2(est.cpu(), gold) < BF16_REL_TOL
+    ours = si_snr_db(est.cpu(), src)
+    ref = si_snr_db(gold, src)
+    assert (ours - ref).abs().max().item() < BF16_SISNR_TOL_DB
+
+
+def test_forward_fp32_matches_oracle_on_fresh_inputs():
+    """Beyond the fixtures: B=3, T % 8 != 0, oracle run live on the same seeded inputs."""
+    sd = synth.make_state_dict("contsep", 2, seed=77)
+    mix, src = synth.make_mixture(3, 5001, 2, seed=78)
+    ctx = synth.make_context(3, 1, seed=78)
+    m = ContSep(2, add_mt=True)
+    m.add_mt_pipeline()
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.precision = "fp32"
+    with torch.no_grad():
+        est, pred = m(mix.to(DEV), ctx.to(DEV))
+        ref_est, ref_pred = O.sepformer_forward(sd, mix, ctx, "contsep", 2)
+    assert rel_l2(est.cpu(), ref_est) < FP32_TOL
+    assert rel_l2(pred.cpu(), ref_pred) < FP32_TOL
+
+
+def test_host_entry_matches_device_entry():
+    """cse_forward_host (pinned host buffers, H2D/D2H inside) == cse_forward."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_b2_t4000")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.precision = "fp32"
+    est, _ = run_model(m, meta, mix, ctx, se)
+    est_h, pred_h = m.separate_host(mix.pin_memory(), ctx.pin_memory())
+    assert torch.equal(est_h, est.cpu())
+    assert pred_h is not None and pred_h.shape == (2, 256)
+
+
+def test_submodule_api_shapes_and_values():
+    """Encoder / Dual_Path_Model_CSE / Decoder used separately, as ContSep.py:69-86 composes them."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_bce_b1_t2024")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        mix_w = m.encoder(mix.to(DEV), precision="fp32")                     # [B,256,L]
+        assert mix_w.shape == (1, 256, (2024 - 16) // 8 + 1)
+        assert rel_l2(mix_w.cpu(), O.encoder(sd, mix)) < 1e-6
+        mask, pred_head = m.masknet(mix_w, ctx.to(DEV), precision="fp32")    # [spk,B,N,L]
+        ref_mask, ref_ph = O.masknet(sd, O.encoder(sd, mix), ctx, 2)
+        assert mask.shape == ref_mask.shape
+        assert rel_l2(mask.cpu(), ref_mask) < FP32_TOL
+        assert rel_l2(pred_head.cpu(), ref_ph) < FP32_TOL
+        dec = m.decoder((mix_w * mask[0]))
+        assert rel_l2(dec.cpu(), O.decoder(sd, O.encoder(sd, mix) * ref_mask[0])) < FP32_TOL
+        blk = m.masknet.dual_mdl[1].inter_mdl
+        x = torch.randn(5, 37, 256, generator=torch.Generator().manual_seed(3))
+        y = blk(x.to(DEV), precision="fp32")
+        ref = O.transformer_block(sd, "masknet.dual_mdl.1.inter_mdl.", x)
+        assert rel_l2(y.cpu(), ref) < 2e-5
+        y16 = blk(x.to(DEV), precision="bf16")
+        assert rel_l2(y16.cpu(), ref) < 3e-2
+
+
+def test_errors_are_python_exceptions():
+    m = PlainSepformer(2).to(DEV).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 8, device=DEV))                  # shorter than the encoder kernel
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4000))                           # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        m.decoder(torch.zeros(1, 1, 256, 10, device=DEV))  # speechbrain Decoder's own check

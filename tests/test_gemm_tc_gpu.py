@@ -1,0 +1,78 @@
+"""GPU: the tcgen05/TMA bf16 GEMM against a float64 product of the same bf16-rounded operands."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+import cse_b200  # noqa: F401
+from cse_b200 import _lib
+from cse_b200._lib import BF16
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _rand(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+SHAPES = [(128, 256, 256), (1, 256, 256), (130, 768, 256), (1000, 1024, 256), (517, 256, 1024),
+          (4099, 512, 256), (300, 128, 64), (20000, 768, 256), (2 * 148 * 128 + 77, 256, 256)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tc_epilogues(M, N, K):
+    A = _rand(M, K, seed=1).to(torch.bfloat16)
+    W = (_rand(N, K, seed=2) / math.sqrt(K)).to(torch.bfloat16)
+    bias = _rand(N, seed=3)
+    res = _rand(M, N, seed=4)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    exact = A.double() @ W.double().t()
+    # bf16 out, bias
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_linear", _lib.ptr(Ad), K, _lib.ptr(Wd), _lib.ptr(bd), 1.0, None, _lib.ptr(out), N,
+              M, N, K, 0, 0, BF16, _st())
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), exact + bias.double()) < 4e-3          # bf16 output rounding
+    # bf16 out, relu, doubled bias
+    _lib.call("cse_linear", _lib.ptr(Ad), K, _lib.ptr(Wd), _lib.ptr(bd), 2.0, None, _lib.ptr(out), N,
+              M, N, K, 1, 0, BF16, _st())
+    assert rel_l2(out.float().cpu(), torch.relu(exact + 2 * bias.double())) < 4e-3
+    # fp32 out, no bias
+    o32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    _lib.call("cse_linear", _lib.ptr(Ad), K, _lib.ptr(Wd), None, 0.0, None, _lib.ptr(o32), N,
+              M, N, K, 0, 1, BF16, _st())
+    assert rel_l2(o32.cpu(), exact) < 1e-5                                   # fp32 accumulate
+    # fp32 in-place residual
+    r = res.to(DEV).clone()
+    _lib.call("cse_linear", _lib.ptr(Ad), K, _lib.ptr(Wd), _lib.ptr(bd), 1.0, _lib.ptr(r), _lib.ptr(r), N,
+              M, N, K, 0, 1, BF16, _st())
+    assert rel_l2(r.cpu(), exact + bias.double() + res.double()) < 1e-5
+
+
+def test_gemm_tc_strided_views():
+    """conv2d output [B*L, spk*256] re-read as [B*L*spk, 256] (abi.cu masknet_impl) and lda > K."""
+    M, K = 777, 256
+    big = _rand(M, 3 * K, seed=5).to(torch.bfloat16).to(DEV)
+    W = (_rand(256, K, seed=6) / 16).to(torch.bfloat16).to(DEV)
+    out = torch.empty(M, 256, dtype=torch.float32, device=DEV)
+    A = big[:, K:2 * K]
+    _lib.call("cse_linear", C.c_void_p(A.data_ptr()), 3 * K, _lib.ptr(W), None, 0.0, None, _lib.ptr(out), 256,
+              M, 256, K, 0, 1, BF16, _st())
+    assert rel_l2(out.cpu(), A.double().cpu() @ W.double().cpu().t()) < 1e-5
+
+
+def test_gemm_tc_rejects_bad_shapes():
+    a = torch.zeros(8, 100, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(256, 100, dtype=torch.bfloat16, device=DEV)
+    o = torch.zeros(8, 256, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.CseError):
+        _lib.call("cse_linear", _lib.ptr(a), 100, _lib.ptr(w), None, 0.0, None, _lib.ptr(o), 256, 8, 256, 100,
+                  0, 0, BF16, _st())
