@@ -49,6 +49,9 @@ class Shape(C.Structure):
 _SIGNATURES = {
     "cse_version": (C.c_int, []),
     "cse_last_error": (C.c_char_p, []),
+    "cse_launch_count": (C.c_longlong, []),
+    "cse_profile_enable": (C.c_int, [C.c_int]),
+    "cse_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "cse_path_shape": (C.c_int, [C.c_int] * 4 + [C.POINTER(Shape)]),
     "cse_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "cse_pack_bf16_elems": (C.c_size_t, [C.c_int]),

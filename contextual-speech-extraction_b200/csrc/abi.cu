@@ -8,6 +8,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace cse {
@@ -21,7 +25,42 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
+// ---- per-kernel-class timing ----
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;       // records of the current collection window
+static std::vector<cudaEvent_t> g_ev_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event() {
+  if (!g_ev_pool.empty()) {
+    cudaEvent_t e = g_ev_pool.back();
+    g_ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+KernelScope::KernelScope(int cls, cudaStream_t st) : slot_(-1), st_(st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  ProfRec r{cls, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  slot_ = (int)g_prof.size() - 1;
+}
+KernelScope::~KernelScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  cudaEventRecord(g_prof[slot_].e1, st_);
+}
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s launch failed: %s", what, cudaGetErrorString(e));
@@ -261,6 +300,31 @@ extern "C" {
 int cse_version(void) { return 100; }
 
 const char* cse_last_error(void) { return g_err; }
+
+long long cse_launch_count(void) { return g_launches.load(); }
+
+int cse_profile_enable(int on) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int cse_profile_collect(double* ms_by_class, long long* launches_by_class, int n_classes) {
+  CSE_REQUIRE(ms_by_class && launches_by_class && n_classes >= kClsCount, "profile_collect: need %d classes", kClsCount);
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+  for (ProfRec& r : g_prof) {
+    CSE_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CSE_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_class[r.cls] += ms;
+    launches_by_class[r.cls] += 1;
+    g_ev_pool.push_back(r.e0);
+    g_ev_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int cse_path_shape(int B, int T, int c, int spk, cse_shape* out) {
   CSE_REQUIRE(out != nullptr, "path_shape: out is NULL");

@@ -273,7 +273,8 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     set_error("attention: nseq=%d exceeds the grid", nseq);
     return 1;
   }
-  dim3 grid((unsigned)nseq * kHeads);  // CTA = (sequence, head); heads of a sequence are adjacent
+  dim3 grid((unsigned)nseq * kHeads);
+  KernelScope prof(kClsAttention, st);  // CTA = (sequence, head); heads of a sequence are adjacent
   if (act == CSE_BF16) {
     const int n_pad = (n + 15) / 16 * 16;
     const size_t smem = (size_t)n_pad * kRowStride * sizeof(bf16) * 2;

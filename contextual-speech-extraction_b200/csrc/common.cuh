@@ -115,6 +115,15 @@ __device__ __forceinline__ void ln_row(f8& x, const f8& g, const f8& b, float ep
   for (int i = 0; i < 8; ++i) x.v[i] = x.v[i] * rstd * g.v[i] + b.v[i];
 }
 
+// ---- optional per-kernel-class device timing (bench.py roofline leg; off by default) ----
+enum KernelClass { kClsGemmTc = 0, kClsAttention = 1, kClsLayerNorm = 2, kClsGemmSimt = 3, kClsCount = 4 };
+struct KernelScope {  // records a CUDA event pair around the launches made in its lifetime
+  KernelScope(int cls, cudaStream_t st);
+  ~KernelScope();
+  int slot_;
+  cudaStream_t st_;
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -136,6 +136,7 @@ int launch_gemm_simt(const float* A, int lda, const float* W, const float* bias,
   }
   if (M <= 0) return 0;
   dim3 grid(N / kBN, ceil_div(M, kBM));
+  KernelScope prof(kClsGemmSimt, st);
   gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W, bias, bias_scale, residual, C, ldc, M, N, K,
                                          relu);
   return check_launch("gemm_simt_kernel");

@@ -146,7 +146,9 @@ struct TcCfg {
   static constexpr int kBBytes = BN * kTK * 2;   // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256;
+  static constexpr int kEpiStageBytes = 4 * 32 * 128;  // 4 epilogue warps x 32 rows x 128 B
+  static constexpr size_t kSmem =
+      1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 + kEpiStageBytes;
 };
 
 template <int BN, bool OUT_F32>
@@ -241,19 +243,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue warps 2..5 =================
+    // TMEM -> registers gives one output ROW per thread; writing that straight to global memory
+    // costs 32 scattered 16-byte requests per instruction.  Each warp instead bounces its 32x32
+    // chunk through a private, XOR-swizzled shared-memory tile and re-reads it with lanes running
+    // along the row, so every global load/store instruction covers whole 128-byte lines.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    unsigned char* stg_base = smem_dyn + ((sBar + 256) - smem_u32(smem_dyn)) + (warp - 2) * (32 * 128);
     uint32_t astage = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
-      const int row = m0 + quarter * 32 + lane;
+      const int row_base = m0 + quarter * 32;
       mbar_wait(bar_tfull + 8 * astage, aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + astage * BN;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
+        const int col0 = n0 + cc * 32;
+        // Residual rows are fetched first (coalesced, 4 rows x 128 B per instruction) so their
+        // latency hides behind the TMEM load and the staging; loads must not be interleaved with
+        // the stores below because C may alias the residual (in-place update of the stream).
+        float4 r4[8];
+        if constexpr (OUT_F32) {
+          if (residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int grow = row_base + j * 4 + (lane >> 3);
+              r4[j] = (grow < M) ? *reinterpret_cast<const float4*>(residual + (size_t)grow * ldc + col0 + (lane & 7) * 4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
         float v[32];
         tmem_ld32(t_row + cc * 32, v);
-        const int col0 = n0 + cc * 32;
         if (bias != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -268,33 +289,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (row < M) {
-          if constexpr (OUT_F32) {
-            float* crow = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + col0;
-            if (residual != nullptr) {
-              const float* rrow = residual + (size_t)row * ldc + col0;
+        if constexpr (OUT_F32) {
+          // stage: row = lane, 8 x 16-byte chunks, chunk index XOR (row & 7)
+          float4* stg = reinterpret_cast<float4*>(stg_base);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rrow + i);
-                v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+          for (int i = 0; i < 8; ++i)
+            stg[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+          const int c4 = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = j * 4 + (lane >> 3);
+            float4 x = stg[rr * 8 + (c4 ^ (rr & 7))];
+            const int grow = row_base + rr;
+            if (grow < M) {
+              const size_t off = (size_t)grow * ldc + col0 + c4 * 4;
+              if (residual != nullptr) {
+                x.x += r4[j].x; x.y += r4[j].y; x.z += r4[j].z; x.w += r4[j].w;
               }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            bf16* crow = reinterpret_cast<bf16*>(Cout) + (size_t)row * ldc + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              h[0] = __floats2bfloat162_rn(v[i], v[i + 1]);
-              h[1] = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-              h[2] = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-              h[3] = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-              *reinterpret_cast<uint4*>(crow + i) = u;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(Cout) + off) = x;
             }
           }
+          __syncwarp();
+        } else {
+          // bf16: 64 B per row = 4 chunks, chunk index XOR ((row >> 1) & 3)
+          uint4* stg = reinterpret_cast<uint4*>(stg_base);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+            h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+            h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+            h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+            stg[lane * 4 + (i ^ ((lane >> 1) & 3))] = u;
+          }
+          __syncwarp();
+          const int c = lane & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = j * 8 + (lane >> 2);
+            const uint4 x = stg[rr * 4 + (c ^ ((rr >> 1) & 3))];
+            const int grow = row_base + rr;
+            if (grow < M)
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(Cout) + (size_t)grow * ldc + col0 + c * 8) = x;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -418,6 +458,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   const int tiles = ceil_div(M, kTM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  KernelScope prof(kClsGemmTc, st);
   gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, bias, bias_scale,
                                                                       residual, C, ldc, M, N, K, relu);
   return check_launch("gemm_tc_kernel");

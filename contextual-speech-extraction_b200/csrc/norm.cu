@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 int launch_layernorm(const float* x, const float* g, const float* b, int M, float eps, int act,
                      void* out, cudaStream_t st) {
   const int grid = (int)min((size_t)148 * 8, ((size_t)M + 7) / 8);
+  KernelScope prof(kClsLayerNorm, st);
   if (act == CSE_BF16)
     layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (bf16*)out);
   else

@@ -109,6 +109,14 @@ typedef struct {
 CSE_API int cse_version(void);
 CSE_API const char* cse_last_error(void);
 
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+CSE_API long long cse_launch_count(void);
+/* Optional device timing per kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 fp32 SIMT
+ * GEMM): while enabled, each launch of those classes is bracketed by a CUDA event pair on its
+ * stream; cse_profile_collect sums and clears them (synchronises on the recorded events). */
+CSE_API int cse_profile_enable(int on);
+CSE_API int cse_profile_collect(double* ms_by_class, long long* launches_by_class, int n_classes);
+
 /* ---- shape algebra (ContSep.py:270-335 `_padding/_Segmentation`; encoder/decoder lengths) ---- */
 typedef struct {
   int B, T, c, spk;

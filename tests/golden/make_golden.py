@@ -59,6 +59,18 @@ def main():
             arrays["est"], arrays["context_pred"] = out[0].numpy(), out[1].numpy()
         else:
             arrays["est"] = out.numpy()
+        # The reference's own reduced-precision path (its --bf16 switch, train_ContSep.py:383), run
+        # here under CPU autocast because this container has no GPU: the yardstick for how far a
+        # bf16 implementation of this network may drift from the fp32 output.
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            if variant == "sepformer":
+                out16 = model(mix)
+            elif variant == "hcontext":
+                out16 = model(mix, ctx, se, cue=cue)
+            else:
+                out16 = model(mix, ctx)
+        out16 = out16[0] if isinstance(out16, tuple) else out16
+        arrays["est_bf16_ref"] = out16.float().numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
         print(name, {k: v.shape for k, v in arrays.items()}, float(np.abs(arrays["est"]).mean()))
 

@@ -21,8 +21,21 @@ def _st():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_KEEP = []
+
+
 def _p(t):
+    """Pointer of a tensor that is kept alive until the test ends (a temporary `.to(DEV)` would be
+    freed — and its memory reused by the next temporary — before the kernel runs)."""
+    _KEEP.append(t)
     return _lib.ptr(t)
+
+
+@pytest.fixture(autouse=True)
+def _release_kept_tensors():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def _rand(*shape, seed=0, scale=1.0):
