@@ -9,9 +9,13 @@
 //  * CSE_FP32: SIMT kernel, K/V of one (sequence, head) staged in shared memory, one thread per
 //    query row, exact expf, fp32 accumulate.
 //  * CSE_BF16: tensor-core kernel (mma.sync.m16n8k16 bf16, fp32 accumulate), online softmax in
-//    registers with exp2, P kept in registers as the A operand of P*V (never written to memory).
-//    K staged row-major, V read through ldmatrix.trans.  Attention is ~10 % of the path's FLOPs
-//    and exp-bound at d=32, so this kernel is written for the SFU/LSU balance, not UMMA tiles.
+//    registers with ex2.approx, P kept in registers as the A operand of P*V (never written to
+//    memory).  Q/K staged row-major (ldmatrix), V read through ldmatrix.trans.  At d=32 the kernel
+//    is bound by the exp (MUFU) and issue rate, not by tensor throughput (QK^T + PV are ~10 % of
+//    the path's FLOPs), so it is written to minimise instructions per score:
+//    FMNMX + FFMA + MUFU.EX2 + FADD + 1/2 CVT.
+//    Short sequences (inter stack at 2-8 s of audio, n <= 64) put all 8 heads of a sequence in
+//    one CTA (one warp per head); long ones use one CTA per (sequence, head).
 #include "common.cuh"
 
 namespace cse {
@@ -106,7 +110,11 @@ __global__ void __launch_bounds__(kAttnThreads) attention_f32_kernel(const float
 // ------------------------------------------------------------------------------------------
 // bf16 tensor-core (mma.sync m16n8k16)
 // ------------------------------------------------------------------------------------------
-constexpr int kRowStride = 40;  // bf16 per staged K/V row (32 + 8 pad): conflict-free LDS/ldmatrix
+// Staged Q/K/V rows are 64 B (32 bf16) with NO padding; the 16-byte chunk index is XOR-swizzled
+// with ((row >> 1) & 3) so that the 8 row addresses of every ldmatrix hit 8 distinct bank groups.
+__device__ __forceinline__ const bf16* sw_ptr(const bf16* base, int row, int chunk) {
+  return base + row * 32 + ((chunk ^ ((row >> 1) & 3)) << 3);
+}
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
                                                uint32_t b1) {
@@ -122,148 +130,205 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attention_bf16_kernel(const bf16* __restrict__ qkv,
-                                                                      int n, int n_pad,
-                                                                      bf16* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* Ks = reinterpret_cast<bf16*>(smem_raw);        // [n_pad][40]
-  bf16* Vs = Ks + (size_t)n_pad * kRowStride;           // [n_pad][40]
-  const int h = blockIdx.x % kHeads;
-  const size_t seq = blockIdx.x / kHeads;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+struct TileState {
+  float o[4][4];
+  float m0, m1, l0, l1;  // running max (scaled log2 domain) and row sums
+};
+
+// One block of 16*NP keys (NP <= 4 pairs of 8-key tiles) for a 16-row query tile.  kTail: keys >= n
+// are masked.  Everything is compile-time unrolled: 4*NP QK^T HMMAs, 16*NP scores per lane,
+// 4*NP PV HMMAs.
+template <int NP, bool kTail>
+__device__ __forceinline__ void attn_block(TileState& st, const uint32_t (&qa)[2][4], const bf16* Ks,
+                                           const bf16* Vs, int j0, int n, int lane) {
+  const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
+  const int t4 = lane & 3;
+  float s[2 * NP][4];
+#pragma unroll
+  for (int np = 0; np < NP; ++np) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[2 * np][e] = s[2 * np + 1][e] = 0.f;
+    // K fragments (B operand): matrices (keys 0-7,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 0-7)
+    // (keys 8-15,d 8-15) for k-step 0; d + 16 for k-step 1
+    const int krow = j0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
+    const int kch = (lane >> 3) & 1;
+    uint32_t kb0[4], kb1[4];
+    ldmatrix_x4(kb0, sw_ptr(Ks, krow, kch));
+    ldmatrix_x4(kb1, sw_ptr(Ks, krow, kch + 2));
+    mma_bf16_16816(s[2 * np], qa[0], kb0[0], kb0[1]);
+    mma_bf16_16816(s[2 * np + 1], qa[0], kb0[2], kb0[3]);
+    mma_bf16_16816(s[2 * np], qa[1], kb1[0], kb1[1]);
+    mma_bf16_16816(s[2 * np + 1], qa[1], kb1[2], kb1[3]);
+  }
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 2 * NP; ++nt) {
+    if (kTail) {
+      const int key = j0 + nt * 8 + t4 * 2;
+      if (key >= n) s[nt][0] = s[nt][2] = -INFINITY;
+      if (key + 1 >= n) s[nt][1] = s[nt][3] = -INFINITY;
+    }
+    bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+    bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+  const float mn0 = fmaxf(st.m0, bm0 * sl2), mn1 = fmaxf(st.m1, bm1 * sl2);  // finite: key j0 < n
+  const float c0 = ex2_approx(st.m0 - mn0), c1 = ex2_approx(st.m1 - mn1);
+  st.l0 *= c0;
+  st.l1 *= c1;
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    st.o[dt][0] *= c0;
+    st.o[dt][1] *= c0;
+    st.o[dt][2] *= c1;
+    st.o[dt][3] *= c1;
+  }
+  st.m0 = mn0;
+  st.m1 = mn1;
+#pragma unroll
+  for (int kt = 0; kt < NP; ++kt) {  // 16 keys per step
+    float p[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      p[u][0] = ex2_approx(fmaf(s[kt * 2 + u][0], sl2, -mn0));
+      p[u][1] = ex2_approx(fmaf(s[kt * 2 + u][1], sl2, -mn0));
+      p[u][2] = ex2_approx(fmaf(s[kt * 2 + u][2], sl2, -mn1));
+      p[u][3] = ex2_approx(fmaf(s[kt * 2 + u][3], sl2, -mn1));
+      st.l0 += p[u][0] + p[u][1];
+      st.l1 += p[u][2] + p[u][3];
+    }
+    uint32_t pa[4];
+    pa[0] = pack_bf16(p[0][0], p[0][1]);
+    pa[1] = pack_bf16(p[0][2], p[0][3]);
+    pa[2] = pack_bf16(p[1][0], p[1][1]);
+    pa[3] = pack_bf16(p[1][2], p[1][3]);
+    // V fragments via ldmatrix.trans: (keys 0-7,d0) (keys 8-15,d0) (keys 0-7,d0+8) (keys 8-15,d0+8)
+    const int vrow = j0 + kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+    const int vch = lane >> 4;
+    uint32_t v0[4], v1[4];
+    ldmatrix_x4_trans(v0, sw_ptr(Vs, vrow, vch));
+    ldmatrix_x4_trans(v1, sw_ptr(Vs, vrow, vch + 2));
+    mma_bf16_16816(st.o[0], pa, v0[0], v0[1]);
+    mma_bf16_16816(st.o[1], pa, v0[2], v0[3]);
+    mma_bf16_16816(st.o[2], pa, v1[0], v1[1]);
+    mma_bf16_16816(st.o[3], pa, v1[2], v1[3]);
+  }
+}
+
+// One 16-row query tile of one head against all n keys.  Qs/Ks/Vs: staged [n_pad][32] bf16
+// (swizzled, pad rows zero).  Writes out rows r < n.
+__device__ __forceinline__ void attn_tile(const bf16* Qs, const bf16* Ks, const bf16* Vs, int mt, int n,
+                                          int n_pad, int lane, bf16* __restrict__ out_rows) {
+  const int g = lane >> 2, t4 = lane & 3;
+  // Q fragments (A operand): ldmatrix x4 = (rows 0-7,k0) (rows 8-15,k0) (rows 0-7,k0+8) (rows 8-15,k0+8)
+  uint32_t qa[2][4];
+  {
+    const int qrow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int qch = lane >> 4;
+    ldmatrix_x4(qa[0], sw_ptr(Qs, qrow, qch));
+    ldmatrix_x4(qa[1], sw_ptr(Qs, qrow, qch + 2));
+  }
+  TileState st;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st.o[i][j] = 0.f;
+  st.m0 = st.m1 = -INFINITY;
+  st.l0 = st.l1 = 0.f;
+
+  const int n_full = n >> 6;  // unmasked 64-key blocks
+  int j0 = 0;
+  for (int b = 0; b < n_full; ++b, j0 += 64) attn_block<4, false>(st, qa, Ks, Vs, j0, n, lane);
+  const int rem = (n_pad - j0) >> 4;  // 16-key pairs left (0..4), masked
+  if (rem == 4) attn_block<4, true>(st, qa, Ks, Vs, j0, n, lane);
+  else if (rem == 3) attn_block<3, true>(st, qa, Ks, Vs, j0, n, lane);
+  else if (rem == 2) attn_block<2, true>(st, qa, Ks, Vs, j0, n, lane);
+  else if (rem == 1) attn_block<1, true>(st, qa, Ks, Vs, j0, n, lane);
+
+  float l0 = st.l0, l1 = st.l1;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    const int col = dt * 8 + t4 * 2;
+    if (r0 < n) *reinterpret_cast<uint32_t*>(out_rows + (size_t)r0 * kN + col) = pack_bf16(st.o[dt][0] * i0, st.o[dt][1] * i0);
+    if (r1 < n) *reinterpret_cast<uint32_t*>(out_rows + (size_t)r1 * kN + col) = pack_bf16(st.o[dt][2] * i1, st.o[dt][3] * i1);
+  }
+}
+
+// HPC = heads per CTA (1: eight warps share one head's query tiles; 8: one warp per head).
+template <int HPC>
+__global__ void __launch_bounds__(256)
+attention_bf16_kernel(const bf16* __restrict__ qkv, int n, int n_pad, bf16* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kThreads = 256;
+  bf16* S = reinterpret_cast<bf16*>(smem_raw);  // [HPC][3][n_pad][32]
+  const int h0 = (HPC == 1) ? (int)(blockIdx.x % kHeads) : 0;
+  const size_t seq = (HPC == 1) ? blockIdx.x / kHeads : blockIdx.x;
   const bf16* base = qkv + seq * n * (3 * kN);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const size_t mat = (size_t)n_pad * 32;
 
-  // stage K and V rows of this head: 4 x 16-byte chunks per row each; pad rows are zero
-  for (int i = threadIdx.x; i < n_pad * 4; i += kAttnThreads) {
-    const int j = i >> 2, ch = i & 3;
-    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
+  // stage Q, K, V rows: 16-byte chunks, coalesced along each row's 64 B; pad rows zero
+  const int chunks = HPC * 3 * n_pad * 4;
+  for (int i = threadIdx.x; i < chunks; i += kThreads) {
+    const int ch = i & 3;
+    int t = i >> 2;
+    const int hh = t % HPC;  // head varies fastest after the chunk: HPC*64 contiguous bytes per (row, matrix)
+    t /= HPC;
+    const int j = t % n_pad, which = t / n_pad;
+    bf16* dst = S + ((size_t)hh * 3 + which) * mat + j * 32 + ((ch ^ ((j >> 1) & 3)) << 3);
     if (j < n) {
-      kv = *reinterpret_cast<const uint4*>(base + (size_t)j * (3 * kN) + kN + h * kDh + ch * 8);
-      vv = *reinterpret_cast<const uint4*>(base + (size_t)j * (3 * kN) + 2 * kN + h * kDh + ch * 8);
+      // cp.async (LDGSTS): every chunk of the CTA is in flight at once instead of one
+      // load->store round trip per loop iteration
+      const bf16* src = base + (size_t)j * (3 * kN) + which * kN + (h0 + hh) * kDh + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                   "l"(src)
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
-    *reinterpret_cast<uint4*>(Ks + j * kRowStride + ch * 8) = kv;
-    *reinterpret_cast<uint4*>(Vs + j * kRowStride + ch * 8) = vv;
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
 
-  const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
-  const int g = lane >> 2, t4 = lane & 3;
   const int n_mt = (n + 15) >> 4;
-  for (int mt = wid; mt < n_mt; mt += kAttnThreads / 32) {
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    // Q fragments: 2 k-steps of 16 over d=32
-    uint32_t qa[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int col = h * kDh + ks * 16 + t4 * 2;
-      qa[ks][0] = (r0 < n) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * (3 * kN) + col) : 0u;
-      qa[ks][1] = (r1 < n) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * (3 * kN) + col) : 0u;
-      qa[ks][2] = (r0 < n) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * (3 * kN) + col + 8) : 0u;
-      qa[ks][3] = (r1 < n) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * (3 * kN) + col + 8) : 0u;
-    }
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-
-    for (int j0 = 0; j0 < n_pad; j0 += 64) {
-      const int nt_cnt = min(8, (n_pad - j0) >> 3);  // 8-key tiles in this block (even number)
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        if (nt < nt_cnt) {
-          const bf16* kr = Ks + (j0 + nt * 8 + g) * kRowStride + t4 * 2;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-            mma_bf16_16816(s[nt], qa[ks], b0, b1);
-          }
-        }
-      }
-      // scale to log2 domain, mask keys >= n, block row max
-      float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int key = j0 + nt * 8 + t4 * 2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool valid = (nt < nt_cnt) && (key + (e & 1) < n);
-          s[nt][e] = valid ? s[nt][e] * sl2 : -INFINITY;
-        }
-        bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
-        bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-      const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);  // finite: every block has key j0 < n
-      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
-      l0 *= c0;
-      l1 *= c1;
-#pragma unroll
-      for (int dt = 0; dt < 4; ++dt) {
-        o[dt][0] *= c0;
-        o[dt][1] *= c0;
-        o[dt][2] *= c1;
-        o[dt][3] *= c1;
-      }
-      m0 = mn0;
-      m1 = mn1;
-      // P = exp2(s - m), row sums in fp32, P packed to bf16 A fragments; O += P V
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {  // 16 keys per step
-        if (kt * 2 < nt_cnt) {
-          uint32_t pa[4];
-          float p[2][4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            p[u][0] = exp2f(s[kt * 2 + u][0] - mn0);
-            p[u][1] = exp2f(s[kt * 2 + u][1] - mn0);
-            p[u][2] = exp2f(s[kt * 2 + u][2] - mn1);
-            p[u][3] = exp2f(s[kt * 2 + u][3] - mn1);
-            l0 += p[u][0] + p[u][1];
-            l1 += p[u][2] + p[u][3];
-          }
-          pa[0] = pack_bf16(p[0][0], p[0][1]);
-          pa[1] = pack_bf16(p[0][2], p[0][3]);
-          pa[2] = pack_bf16(p[1][0], p[1][1]);
-          pa[3] = pack_bf16(p[1][2], p[1][3]);
-          // V fragments via ldmatrix.trans: matrices (keys 0-7,d0) (keys 8-15,d0) (keys 0-7,d0+8)
-          // (keys 8-15,d0+8); lane -> row address of matrix lane/8, row lane%8
-          const int key = j0 + kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-#pragma unroll
-          for (int dp = 0; dp < 2; ++dp) {  // d tiles (0,1) then (2,3)
-            const bf16* vp = Vs + key * kRowStride + dp * 16 + (lane >> 4) * 8;
-            const uint32_t addr = (uint32_t)__cvta_generic_to_shared(vp);
-            uint32_t v0, v1, v2, v3;
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                         : "r"(addr));
-            mma_bf16_16816(o[dp * 2], pa, v0, v1);
-            mma_bf16_16816(o[dp * 2 + 1], pa, v2, v3);
-          }
-        }
-      }
-    }
-    // finalise: quad-reduce the row sums, normalise, store bf16 pairs
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-#pragma unroll
-    for (int dt = 0; dt < 4; ++dt) {
-      const int col = h * kDh + dt * 8 + t4 * 2;
-      if (r0 < n)
-        *reinterpret_cast<uint32_t*>(out + (seq * n + r0) * kN + col) = pack_bf16(o[dt][0] * i0, o[dt][1] * i0);
-      if (r1 < n)
-        *reinterpret_cast<uint32_t*>(out + (seq * n + r1) * kN + col) = pack_bf16(o[dt][2] * i1, o[dt][3] * i1);
-    }
+  if (HPC == 1) {
+    const bf16* Qs = S;
+    const bf16* Ks = S + mat;
+    const bf16* Vs = S + 2 * mat;
+    bf16* orow = out + seq * n * kN + h0 * kDh;
+    for (int mt = wid; mt < n_mt; mt += kThreads / 32) attn_tile(Qs, Ks, Vs, mt, n, n_pad, lane, orow);
+  } else {
+    const bf16* Qs = S + (size_t)wid * 3 * mat;
+    bf16* orow = out + seq * n * kN + wid * kDh;
+    for (int mt = 0; mt < n_mt; ++mt) attn_tile(Qs, Qs + mat, Qs + 2 * mat, mt, n, n_pad, lane, orow);
   }
 }
 
@@ -273,22 +338,27 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     set_error("attention: nseq=%d exceeds the grid", nseq);
     return 1;
   }
-  dim3 grid((unsigned)nseq * kHeads);
-  KernelScope prof(kClsAttention, st);  // CTA = (sequence, head); heads of a sequence are adjacent
+  KernelScope prof(kClsAttention, st);
   if (act == CSE_BF16) {
     const int n_pad = (n + 15) / 16 * 16;
-    const size_t smem = (size_t)n_pad * kRowStride * sizeof(bf16) * 2;
     static bool configured = false;
     if (!configured) {
-      cudaFuncSetAttribute(attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(attention_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(attention_bf16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured = true;
     }
+    if (n <= 64) {  // all 8 heads of a sequence in one CTA, one warp per head
+      const size_t smem = (size_t)8 * 3 * n_pad * 32 * sizeof(bf16);
+      attention_bf16_kernel<8><<<nseq, 256, smem, st>>>((const bf16*)qkv, n, n_pad, (bf16*)out);
+      return check_launch("attention_bf16_kernel<8>");
+    }
+    const size_t smem = (size_t)3 * n_pad * 32 * sizeof(bf16);
     if (smem > 200 * 1024) {
       set_error("attention: sequence of %d tokens does not fit shared memory", n);
       return 1;
     }
-    attention_bf16_kernel<<<grid, kAttnThreads, smem, st>>>((const bf16*)qkv, n, n_pad, (bf16*)out);
-    return check_launch("attention_bf16_kernel");
+    attention_bf16_kernel<1><<<(unsigned)nseq * kHeads, 256, smem, st>>>((const bf16*)qkv, n, n_pad, (bf16*)out);
+    return check_launch("attention_bf16_kernel<1>");
   }
   const size_t smem = (size_t)n * kDh * sizeof(float) * 2;
   static bool configured32 = false;
@@ -300,7 +370,7 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     set_error("attention: sequence of %d tokens does not fit shared memory (fp32)", n);
     return 1;
   }
-  attention_f32_kernel<<<grid, kAttnThreads, smem, st>>>((const float*)qkv, n, (float*)out);
+  attention_f32_kernel<<<(unsigned)nseq * kHeads, kAttnThreads, smem, st>>>((const float*)qkv, n, (float*)out);
   return check_launch("attention_f32_kernel");
 }
 

@@ -12,8 +12,10 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
 //                 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the
 //                 MMAs of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32 columns), bias / ReLU / fp32 residual,
-//                 vector stores (one output row per thread)
+//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / bf16 pack ->
+//                 128B-swizzled shared-memory chunk -> TMA store.  The fp32 residual update
+//                 R += A W^T + b is a TMA REDUCE-ADD (cp.reduce.async.bulk.tensor .add), so the
+//                 residual stream is never loaded into the SM; the M tail is clipped by TMA.
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
@@ -27,7 +29,7 @@ namespace cse {
 constexpr int kTM = 128;  // UMMA M
 constexpr int kTK = 64;   // K per stage: 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // producer + MMA + 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -75,6 +77,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
@@ -141,35 +164,37 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 4;
   static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kTK * 2;   // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
-  static constexpr int kEpiStageBytes = 4 * 32 * 128;  // 4 epilogue warps x 32 rows x 128 B
-  static constexpr size_t kSmem =
-      1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 + kEpiStageBytes;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiBufBytes = 32 * 128;  // one chunk: 32 rows x 128 B
+  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;  // double-buffered per warp
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256;
 };
 
 template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, float bias_scale, const float* residual, void* Cout,
-               int ldc, int M, int N, int K, int relu) {
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
+               float bias_scale, int accumulate_into_c, int M, int N, int K, int relu) {
   using Cfg = TcCfg<BN>;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + Cfg::kStages * Cfg::kABytes;
-  const uint32_t sBar = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t sEpi = smem_base + Cfg::kStages * Cfg::kStageBytes;  // multiple of 1024
+  const uint32_t sBar = sEpi + Cfg::kEpiBytes;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
   const uint32_t bar_full = sBar;
   const uint32_t bar_empty = sBar + 8 * Cfg::kStages;
   const uint32_t bar_tfull = sBar + 16 * Cfg::kStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+  unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kTM - 1) / kTM, n_tiles = N / BN;
@@ -183,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -242,14 +267,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
   } else {
-    // ================= epilogue warps 2..5 =================
-    // TMEM -> registers gives one output ROW per thread; writing that straight to global memory
-    // costs 32 scattered 16-byte requests per instruction.  Each warp instead bounces its 32x32
-    // chunk through a private, XOR-swizzled shared-memory tile and re-reads it with lanes running
-    // along the row, so every global load/store instruction covers whole 128-byte lines.
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
-    unsigned char* stg_base = smem_dyn + ((sBar + 256) - smem_u32(smem_dyn)) + (warp - 2) * (32 * 128);
-    uint32_t astage = 0, aphase = 0;
+    // ================= epilogue warps 2..9 =================
+    // warp -> TMEM lane quarter (warp & 3, fixed by hardware) x column half ((warp-2) >> 2).
+    // Per chunk: TMEM -> registers (one output row per thread) -> bias/ReLU/pack -> warp-private
+    // SWIZZLE_128B staging tile -> one elected lane issues a TMA store (or reduce-add).  Two
+    // staging buffers per warp: the store of chunk i overlaps the TMEM load of chunk i+1.
+    constexpr int CW = OUT_F32 ? 32 : 64;        // columns per chunk = 128 B per row
+    constexpr int NCH = (BN / 2) / CW;
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t stg0 = sEpi + (warp - 2) * 2 * Cfg::kEpiBufBytes;
+    unsigned char* stg0_ptr = smem_aligned + (stg0 - smem_base);
+    uint32_t astage = 0, aphase = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
       const int row_base = m0 + quarter * 32;
@@ -257,84 +286,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + astage * BN;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        const int col0 = n0 + cc * 32;
-        // Residual rows are fetched first (coalesced, 4 rows x 128 B per instruction) so their
-        // latency hides behind the TMEM load and the staging; loads must not be interleaved with
-        // the stores below because C may alias the residual (in-place update of the stream).
-        float4 r4[8];
-        if constexpr (OUT_F32) {
-          if (residual != nullptr) {
+      for (int ch = 0; ch < NCH; ++ch, ++chunk_ctr) {
+        const int col_local = half * (BN / 2) + ch * CW;
+        const int col0 = n0 + col_local;
+        const uint32_t buf = chunk_ctr & 1u;
+        if (chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        uint4* stg = reinterpret_cast<uint4*>(stg0_ptr + buf * Cfg::kEpiBufBytes);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int grow = row_base + j * 4 + (lane >> 3);
-              r4[j] = (grow < M) ? *reinterpret_cast<const float4*>(residual + (size_t)grow * ldc + col0 + (lane & 7) * 4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int part = 0; part < CW / 32; ++part) {
+          float v[32];
+          tmem_ld32(t_row + col_local + part * 32, v);
+          if (bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
+              v[i] = fmaf(bias_scale, b4.x, v[i]);
+              v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
+              v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
+              v[i + 3] = fmaf(bias_scale, b4.w, v[i + 3]);
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          // row = lane; 16-byte chunk index XOR (row & 7) == the TMA SWIZZLE_128B pattern
+          if constexpr (OUT_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 u;
+              u.x = __float_as_uint(v[4 * i]);
+              u.y = __float_as_uint(v[4 * i + 1]);
+              u.z = __float_as_uint(v[4 * i + 2]);
+              u.w = __float_as_uint(v[4 * i + 3]);
+              stg[lane * 8 + (i ^ (lane & 7))] = u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+              h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+              h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              stg[lane * 8 + ((part * 4 + i) ^ (lane & 7))] = u;
             }
           }
         }
-        float v[32];
-        tmem_ld32(t_row + cc * 32, v);
-        if (bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-            v[i] = fmaf(bias_scale, b4.x, v[i]);
-            v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
-            v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
-            v[i + 3] = fmaf(bias_scale, b4.w, v[i + 3]);
-          }
-        }
-        if (relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if constexpr (OUT_F32) {
-          // stage: row = lane, 8 x 16-byte chunks, chunk index XOR (row & 7)
-          float4* stg = reinterpret_cast<float4*>(stg_base);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            stg[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          __syncwarp();
-          const int c4 = lane & 7;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = j * 4 + (lane >> 3);
-            float4 x = stg[rr * 8 + (c4 ^ (rr & 7))];
-            const int grow = row_base + rr;
-            if (grow < M) {
-              const size_t off = (size_t)grow * ldc + col0 + c4 * 4;
-              if (residual != nullptr) {
-                x.x += r4[j].x; x.y += r4[j].y; x.z += r4[j].z; x.w += r4[j].w;
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(Cout) + off) = x;
-            }
-          }
-          __syncwarp();
-        } else {
-          // bf16: 64 B per row = 4 chunks, chunk index XOR ((row >> 1) & 3)
-          uint4* stg = reinterpret_cast<uint4*>(stg_base);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-            h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-            h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-            h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-            stg[lane * 4 + (i ^ ((lane >> 1) & 3))] = u;
-          }
-          __syncwarp();
-          const int c = lane & 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int rr = j * 8 + (lane >> 2);
-            const uint4 x = stg[rr * 4 + (c ^ ((rr >> 1) & 3))];
-            const int grow = row_base + rr;
-            if (grow < M)
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(Cout) + (size_t)grow * ldc + col0 + c * 8) = x;
-          }
-          __syncwarp();
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t src = stg0 + buf * Cfg::kEpiBufBytes;
+          if (accumulate_into_c)
+            tma_reduce_add_2d(&tmC, src, col0, row_base);
+          else
+            tma_store_2d(&tmC, src, col0, row_base);
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -342,6 +353,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(bar_tempty + 8 * astage);
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
+    if (lane == 0) bulk_wait_all();  // all output writes complete before the CTA retires
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -377,25 +390,28 @@ static EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
-  uint32_t box_rows;
+  uint32_t box_rows, box_cols, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
-    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull + k.box_rows);
+    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull +
+                               k.box_rows * 131ull + k.box_cols * 7ull + k.esize);
     return h;
   }
 };
 
-// bf16 row-major [rows, cols] matrix with leading dimension ld; box = [box_rows x 64 cols], 128B swizzle.
-static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                          uint32_t box_rows, CUtensorMap* out) {
+// Row-major [rows, cols] matrix (bf16 or fp32) with leading dimension ld (elements);
+// box = [box_rows x box_cols] with box_cols * esize == 128 B, SWIZZLE_128B.
+static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                          uint32_t box_cols, uint32_t esize, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld, box_rows};
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols, esize};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -410,16 +426,17 @@ static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_
     return 1;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)kTK, box_rows};
+  cuuint64_t gstride[1] = {ld * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box_rows=%u",
-              (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols,
-              (unsigned long long)ld, box_rows);
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u esize=%u",
+              (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
+              box_rows, box_cols, esize);
     return 1;
   }
   {
@@ -442,9 +459,9 @@ static int sm_count() {
 }
 
 template <int BN, bool OUT_F32>
-static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
-                          float bias_scale, const float* residual, void* C, int ldc, int M, int N,
-                          int K, int relu, cudaStream_t st) {
+static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                          const float* bias, float bias_scale, int accumulate, int M, int N, int K,
+                          int relu, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -459,8 +476,8 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int tiles = ceil_div(M, kTM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   KernelScope prof(kClsGemmTc, st);
-  gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, bias, bias_scale,
-                                                                      residual, C, ldc, M, N, K, relu);
+  gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, tmC, bias, bias_scale,
+                                                                      accumulate, M, N, K, relu);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -473,8 +490,8 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
               M, N, K, lda, ldc);
     return 1;
   }
-  if (residual != nullptr && !out_fp32) {
-    set_error("gemm_tc: a residual needs an fp32 output");
+  if (residual != nullptr && (!out_fp32 || (const void*)residual != (const void*)C)) {
+    set_error("gemm_tc: the residual must be the fp32 output itself (in-place stream update via TMA reduce-add)");
     return 1;
   }
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) {
@@ -482,15 +499,18 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
     return 1;
   }
   const int BN = (N % 256 == 0) ? 256 : 128;
-  CUtensorMap tmA, tmB;
-  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, &tmA)) return 1;
-  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, &tmB)) return 1;
+  CUtensorMap tmA, tmB, tmC;
+  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
+  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, kTK, 2, &tmB)) return 1;
+  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, out_fp32 ? 32 : 64, out_fp32 ? 4 : 2, &tmC))
+    return 1;
+  const int acc = residual != nullptr ? 1 : 0;
   if (BN == 256) {
-    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st);
+    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st);
   }
-  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st)
-                  : launch_tc_impl<128, false>(tmA, tmB, bias, bias_scale, residual, C, ldc, M, N, K, relu, st);
+  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st)
+                  : launch_tc_impl<128, false>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st);
 }
 
 }  // namespace cse

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/quick_time.py 16 32000 bf16 1 > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attention_bf16 -s 7 -c 2 -o gpurun_out/prof_attn -f \
+    python tools/quick_time.py 16 32000 bf16 1 > gpurun_out/ncu_attn.log 2>&1
+echo "ncu attn: exit $?"
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 9 -c 4 -o gpurun_out/prof_gemm -f \
+    python tools/quick_time.py 16 32000 bf16 1 > gpurun_out/ncu_gemm.log 2>&1
+echo "ncu gemm: exit $?"; ls -la gpurun_out/*.ncu-rep
