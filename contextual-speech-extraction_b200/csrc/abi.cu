@@ -303,6 +303,11 @@ const char* cse_last_error(void) { return g_err; }
 
 long long cse_launch_count(void) { return g_launches.load(); }
 
+int cse_debug_force_mma_attention(int on) {
+  g_attention_mode = on;  // 0 auto, 1 force mma.sync, 2 force tcgen05 (n <= 256)
+  return 0;
+}
+
 int cse_profile_enable(int on) {
   std::lock_guard<std::mutex> g(g_prof_mu);
   g_prof_on = on != 0;

@@ -332,6 +332,10 @@ attention_bf16_kernel(const bf16* __restrict__ qkv, int n, int n_pad, bf16* __re
   }
 }
 
+// Test hook (cse_debug_force_mma_attention): route n <= 256 through the long-sequence kernel too, so
+// both attention kernels can be checked against the oracle at the same shapes.
+int g_attention_mode = 0;
+
 int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaStream_t st) {
   if (nseq <= 0 || n <= 0) return 0;
   if ((long long)nseq * kHeads > 2147483647LL) {
@@ -340,6 +344,12 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
   }
   KernelScope prof(kClsAttention, st);
   if (act == CSE_BF16) {
+    // up to 256 tokens the whole score row fits TMEM: tcgen05 kernel (attention_tc.cu); longer
+    // sequences (inter stack beyond ~30 s of audio) use the online-softmax mma.sync kernel below
+    // Very short sequences (inter stack at <= 8 s of audio) are latency- not exp-bound and run
+    // faster with all 8 heads of a sequence in one mma.sync CTA (measured 122 vs 163 us at n = 35).
+    if (n <= 256 && g_attention_mode != 1 && (n > 64 || g_attention_mode == 2))
+      return launch_attention_tc((const bf16*)qkv, nseq, n, (bf16*)out, st);
     const int n_pad = (n + 15) / 16 * 16;
     static bool configured = false;
     if (!configured) {

@@ -1,0 +1,381 @@
+// attention_tc.cu — tcgen05 / TMEM attention for sequences of up to 256 tokens (every intra chunk,
+// and the inter stack up to ~30 s of audio).
+//
+// Reference: nn.MultiheadAttention core = softmax(q k^T / sqrt(32)) v per head, no mask
+// (CSE_transformer.py:535-557 -> torch functional.py:6682).
+//
+// One work item = one 128-row query tile of one head:
+//   * n <= 128 ("packed"): floor(128/n) consecutive sequences share a tile; S is block-diagonal and
+//     every row only exponentiates its own sequence's n keys (the inter stack at 2-16 s of audio).
+//   * 128 < n <= 256 ("split"): two query tiles per sequence against all n keys (the intra stack).
+// Pipeline per item (two items in flight per SM, one per 128-thread warp-group; the group's leader
+// thread issues its own PV MMA, a dedicated warp issues the S MMAs, two producer lanes stream Q/K and V):
+//   TMA (SWIZZLE_64B boxes of the packed qkv buffer: Q 128x32, K/V up to 256x32)
+//   -> tcgen05.mma  S[128 x Ncols] = Q K^T   (both operands K-major, fp32 accumulators in TMEM)
+//   -> 128 softmax threads, ONE ROW EACH: tcgen05.ld the row in 32-column chunks, exact two-pass
+//      softmax (the whole row is on chip, so no online rescaling): FMNMX pass, then
+//      FFMA + MUFU.EX2 + FADD per score, P packed to bf16 into a SWIZZLE_128B K-major smem tile
+//   -> tcgen05.mma  O[128 x 32] = P V        (A = P from smem, B = V as an MN-major operand, so V
+//      is consumed exactly as TMA wrote it; O overwrites the first 32 columns of S in TMEM)
+//   -> the same threads scale O by 1/rowsum and store bf16.
+// The kernel is MUFU-bound by construction (32768 exp per item vs 4+16 UMMA instructions).
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace cse {
+
+using namespace tc;
+
+constexpr int kAtThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax group 0, 6-9 group 1
+constexpr int kAtQ = 128 * 64;        // 8 KB   Q tile  [128 rows x 32 bf16]
+constexpr int kAtKV = 256 * 64;       // 16 KB  K or V  [256 rows x 32 bf16]
+constexpr int kAtP = 4 * 128 * 128;   // 64 KB  P       4 k-blocks of [128 rows x 64 bf16]
+constexpr int kAtBuf = kAtQ + 2 * kAtKV + kAtP;
+constexpr size_t kAtSmem = 1024 + 2 * (size_t)kAtBuf + 256;
+
+struct AtItem {
+  int q_row0, q_rows, kv_row0, kv_rows, head;
+};
+
+__device__ __forceinline__ AtItem at_decode(int item, int n, int nseq, int g) {
+  AtItem it;
+  it.head = item & 7;
+  const int unit = item >> 3;
+  if (g > 0) {  // packed: g sequences per tile
+    const int s0 = unit * g;
+    const int cnt = min(g, nseq - s0);
+    it.q_row0 = it.kv_row0 = s0 * n;
+    it.q_rows = it.kv_rows = cnt * n;
+  } else {      // split: two query tiles per sequence
+    const int seq = unit >> 1, mt = unit & 1;
+    it.q_row0 = seq * n + mt * 128;
+    it.q_rows = min(128, n - mt * 128);
+    it.kv_row0 = seq * n;
+    it.kv_rows = n;
+  }
+  return it;
+}
+
+__device__ __forceinline__ float at_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// max over 64 values with four independent chains (a serial fmaxf chain costs 64 x 4 cycles)
+__device__ __forceinline__ float at_max64(const float (&v)[64]) {
+  float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+  for (int i = 4; i < 64; i += 4) {
+    m0 = fmaxf(m0, v[i]);
+    m1 = fmaxf(m1, v[i + 1]);
+    m2 = fmaxf(m2, v[i + 2]);
+    m3 = fmaxf(m3, v[i + 3]);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
+                    int g, int items) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t sBar = smem_base + 2 * kAtBuf;
+  // per buffer b: qk_full, v_full, s_full, o_full, free  (8 bytes each)
+  auto bar = [&](int which, int b) -> uint32_t { return sBar + (uint32_t)(which * 2 + b) * 8; };
+  enum { QK_FULL = 0, V_FULL = 1, S_FULL = 2, O_FULL = 3, FREE = 4 };
+  const uint32_t tmem_slot = sBar + 10 * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+  auto sQ = [&](int b) { return smem_base + (uint32_t)b * kAtBuf; };
+  auto sK = [&](int b) { return smem_base + (uint32_t)b * kAtBuf + kAtQ; };
+  auto sV = [&](int b) { return smem_base + (uint32_t)b * kAtBuf + kAtQ + kAtKV; };
+  auto sP = [&](int b) { return smem_base + (uint32_t)b * kAtBuf + kAtQ + 2 * kAtKV; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(QK_FULL, b), 1);
+      mbar_init(bar(V_FULL, b), 1);
+      mbar_init(bar(S_FULL, b), 1);
+      mbar_init(bar(O_FULL, b), 1);
+      mbar_init(bar(FREE, b), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producers: lane 0 streams Q/K, lane 1 streams V =================
+    // (separate lanes so a V load that waits for the previous PV-MMA never delays the next Q/K)
+    if (lane < 2) {
+      int k = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+        const int b = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        const AtItem it = at_decode(item, n, nseq, g);
+        const int nk = it.kv_rows > 128 ? 2 : 1;
+        if (lane == 0) {
+          // Q/K of this buffer were last read by the S-MMA of item k-2
+          if (k >= 2) mbar_wait(bar(S_FULL, b), ph ^ 1u, 10);
+          mbar_expect_tx(bar(QK_FULL, b), (uint32_t)(kAtQ + nk * 8192));
+          tma_load_2d(sQ(b), &tmQKV, bar(QK_FULL, b), it.head * kDh, it.q_row0);
+          tma_load_2d(sK(b), &tmQKV, bar(QK_FULL, b), kN + it.head * kDh, it.kv_row0);
+          if (nk == 2) tma_load_2d(sK(b) + 8192, &tmQKV, bar(QK_FULL, b), kN + it.head * kDh, it.kv_row0 + 128);
+        } else {
+          // V of this buffer was last read by the PV-MMA of item k-2
+          if (k >= 2) mbar_wait(bar(O_FULL, b), ph ^ 1u, 11);
+          mbar_expect_tx(bar(V_FULL, b), (uint32_t)(nk * 8192));
+          tma_load_2d(sV(b), &tmQKV, bar(V_FULL, b), 2 * kN + it.head * kDh, it.kv_row0);
+          if (nk == 2) tma_load_2d(sV(b) + 8192, &tmQKV, bar(V_FULL, b), 2 * kN + it.head * kDh, it.kv_row0 + 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= S = Q K^T issuer =================
+    if (lane == 0) {
+      int k = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+        const int b = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        const AtItem it = at_decode(item, n, nseq, g);
+        const int ncols = (it.kv_rows + 15) & ~15;
+        mbar_wait(bar(QK_FULL, b), ph, 22);
+        if (k >= 2) mbar_wait(bar(FREE, b), ph ^ 1u, 23);  // O of item k-2 drained from TMEM
+        fence_after();
+        const uint32_t idesc_s = make_idesc_bf16(128, ncols, 0, 0);
+        const uint64_t ad = make_desc(sQ(b), 512, kLayoutSw64);
+        const uint64_t bd = make_desc(sK(b), 512, kLayoutSw64);
+        const uint32_t d_s = tmem_base + (uint32_t)b * 256;
+        umma_bf16(d_s, ad, bd, idesc_s, 0u);
+        umma_bf16(d_s, ad + 2, bd + 2, idesc_s, 1u);  // second k16 step: +32 B inside the 64-B row
+        umma_commit(bar(S_FULL, b));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + PV + epilogue groups (128 threads each) =================
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+    const int grp = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const bool leader = (warp == 2 + 4 * grp) && lane == 0;
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
+    int k = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+      if ((k & 1) != grp) continue;
+      const int b = grp;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      const AtItem it = at_decode(item, n, nseq, g);
+      const int ncols = (it.kv_rows + 15) & ~15;
+      const int npair = (ncols + 63) >> 6;  // 64-key blocks
+      int lo = 0, hi = it.kv_rows;
+      if (g > 0) {  // packed: this row's own sequence
+        const int sidx = min(r / n, it.q_rows / n - 1);
+        lo = sidx * n;
+        hi = lo + n;
+      }
+      // tcgen05.ld is warp-collective (.sync.aligned): chunk loops must be warp-uniform, so they run
+      // over the union [wlo, whi) of the key ranges of the warp's 32 rows; per-row masks inside.
+      const int wlo = __reduce_min_sync(0xffffffffu, lo);
+      const int whi = __reduce_max_sync(0xffffffffu, hi);
+      const bool uniform = (g == 0);  // split mode: every row of the tile has the same key range
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
+      mbar_wait(bar(S_FULL, b), ph, 30);
+      fence_after();
+      // ---- pass 1: row max over [lo, hi) ----
+      float mx = -INFINITY;
+      for (int cp = wlo >> 6; cp <= (whi - 1) >> 6; ++cp) {
+        float v[64];
+        tmem_ld64(taddr + cp * 64, v);
+        const int c0 = cp * 64;
+        if (!(uniform && c0 + 64 <= hi)) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
+        }
+        mx = fmaxf(mx, at_max64(v));
+      }
+      const float msc = mx * sl2;
+      // ---- pass 2: P = 2^(s*sl2 - m), row sum, bf16 P into the swizzled A-operand tile ----
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      unsigned char* prow = smem_al + (sP(b) - smem_base) + r * 128;
+      for (int cp = 0; cp < npair; ++cp) {
+        const int c0 = cp * 64;
+        uint4* dst = reinterpret_cast<uint4*>(prow + cp * 16384);  // k-block cp: [128 rows x 64 keys]
+        if (c0 + 64 <= wlo || c0 >= whi) {  // warp-uniform: no row of this warp attends these keys
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i ^ (r & 7)] = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
+        float v[64];
+        tmem_ld64(taddr + c0, v);
+        if (uniform && c0 + 64 <= hi) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = at_ex2(fmaf(v[i], sl2, -msc));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float p = at_ex2(fmaf(v[i], sl2, -msc));
+            v[i] = (c0 + i >= lo && c0 + i < hi) ? p : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          sum0 += v[i];
+          sum1 += v[i + 1];
+          sum2 += v[i + 2];
+          sum3 += v[i + 3];
+        }
+        // 16-byte chunk i XOR (row & 7): SWIZZLE_128B K-major
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+          h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+          h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+          h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+          dst[i ^ (r & 7)] = u;
+        }
+      }
+      const float sum = (sum0 + sum1) + (sum2 + sum3);
+      fence_before();        // TMEM reads of S done before the PV MMA overwrites S[:, 0:32] with O
+      fence_proxy_async();   // P (generic-proxy stores) visible to the tensor core's async proxy
+      named_bar_sync(1 + grp, 128);
+      // ---- O = P V, issued by the group's own leader thread ----
+      if (leader) {
+        mbar_wait(bar(V_FULL, b), ph, 21);
+        fence_after();
+        const uint32_t d_o = tmem_base + (uint32_t)b * 256;  // O overwrites S[:, 0:32]
+        for (int t = 0; t < ncols / 16; ++t) {
+          const uint64_t ad = make_desc(sP(b) + (uint32_t)(t >> 2) * 16384, 1024, kLayoutSw128) + (uint64_t)(2 * (t & 3));
+          const uint64_t bd = make_desc(sV(b) + (uint32_t)t * 1024, 512, kLayoutSw64);
+          umma_bf16(d_o, ad, bd, idesc_pv, t > 0 ? 1u : 0u);
+        }
+        umma_commit(bar(O_FULL, b));
+      }
+      __syncwarp();
+      // ---- epilogue: O / rowsum -> bf16 ----
+      mbar_wait(bar(O_FULL, b), ph, 31);
+      fence_after();
+      {
+        float o[32];
+        tmem_ld32(taddr, o);
+        const float inv = 1.0f / sum;
+        if (r < it.q_rows) {
+          uint4* dsto = reinterpret_cast<uint4*>(out + (size_t)(it.q_row0 + r) * kN + it.head * kDh);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            h[0] = __floats2bfloat162_rn(o[8 * i] * inv, o[8 * i + 1] * inv);
+            h[1] = __floats2bfloat162_rn(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+            h[2] = __floats2bfloat162_rn(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+            h[3] = __floats2bfloat162_rn(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+            dsto[i] = u;
+          }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(FREE, b));
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
+  static AtEncodeFn fn = nullptr;
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, CUtensorMap> cache;
+  std::lock_guard<std::mutex> g(mu);
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      set_error("attention_tc: cuTensorMapEncodeTiled is unavailable");
+      return 1;
+    }
+    fn = reinterpret_cast<AtEncodeFn>(p);
+  }
+  const uint64_t key = (uint64_t)(uintptr_t)qkv * 1000003ull + rows;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)(3 * kN), rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)(3 * kN) * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)kDh, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 1;
+  }
+  if (cache.size() > 1024) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_t st) {
+  if (n < 1 || n > 256) {
+    set_error("attention_tc: n=%d outside [1,256]", n);
+    return 1;
+  }
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kAtSmem);
+    if (e != cudaSuccess) {
+      set_error("attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    configured = true;
+  }
+  CUtensorMap tm;
+  if (at_tensor_map(qkv, (uint64_t)nseq * n, &tm)) return 1;
+  const int g = n <= 128 ? 128 / n : 0;
+  const long long units = g > 0 ? ((long long)nseq + g - 1) / g : (long long)nseq * 2;
+  const long long items = units * kHeads;
+  if (items > 2147483647LL) {
+    set_error("attention_tc: too many work items");
+    return 1;
+  }
+  const int grid = (int)(items < sms ? items : sms);
+  attention_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tm, out, n, nseq, g, (int)items);
+  return check_launch("attention_tc_kernel");
+}
+
+}  // namespace cse

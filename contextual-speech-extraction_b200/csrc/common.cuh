@@ -162,6 +162,8 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
                    int out_fp32, cudaStream_t st);
 // attention.cu
 int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaStream_t st);
+int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_t st);  // attention_tc.cu
+extern int g_attention_mode;
 // head.cu
 int launch_prelu_ola(const float* X, const float* prelu, int B, int S, int L, int act, void* U,
                      cudaStream_t st);

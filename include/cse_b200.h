@@ -111,6 +111,9 @@ CSE_API const char* cse_last_error(void);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 CSE_API long long cse_launch_count(void);
+/* Test hook: 0 = automatic choice, 1 = force the mma.sync online-softmax bf16 attention kernel,
+ * 2 = force the tcgen05 kernel (n <= 256) — so both kernels can be checked at the same shapes. */
+CSE_API int cse_debug_force_mma_attention(int on);
 /* Optional device timing per kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 fp32 SIMT
  * GEMM): while enabled, each launch of those classes is bracketed by a CUDA event pair on its
  * stream; cse_profile_collect sums and clears them (synchronises on the recorded events). */

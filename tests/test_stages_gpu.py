@@ -105,14 +105,27 @@ def _attention_ref(qkv, nseq, n):
     return (att @ v).permute(0, 2, 1, 3).reshape(nseq * n, 256)
 
 
-@pytest.mark.parametrize("nseq,n", [(3, 251), (5, 35), (2, 132), (4, 1), (2, 17), (1, 260), (2, 64)])
-@pytest.mark.parametrize("prec", [FP32, BF16])
+@pytest.mark.parametrize("nseq,n", [(3, 251), (5, 35), (2, 132), (4, 1), (2, 17), (1, 260), (2, 64),
+                                    (7, 35), (300, 35), (40, 252), (1, 128), (3, 129), (2, 256), (5, 100)])
+@pytest.mark.parametrize("prec", [FP32, BF16, "bf16-mma", "bf16-tc"])
 def test_attention(nseq, n, prec):
+    """fp32 SIMT kernel, the automatic bf16 choice, and each bf16 kernel forced: tcgen05 (n <= 256;
+    packed tiles for n <= 128, split tiles above) and mma.sync online softmax (any n), all against
+    the float64 softmax(q k^T / sqrt(d)) v."""
+    mode = {"bf16-mma": 1, "bf16-tc": 2}.get(prec, 0)
+    if mode == 2 and n > 256:
+        pytest.skip("tcgen05 attention handles n <= 256")
+    prec = BF16 if mode else prec
     qkv = _rand(nseq * n, 768, seed=12) * 1.5
     adt = torch.bfloat16 if prec == BF16 else torch.float32
     q = qkv.to(adt)
-    out = torch.empty(nseq * n, 256, dtype=adt, device=DEV)
-    _lib.call("cse_attention_fwd", _p(q.to(DEV)), nseq, n, prec, _p(out), _st())
+    out = torch.zeros(nseq * n, 256, dtype=adt, device=DEV)
+    _lib.load().cse_debug_force_mma_attention(mode)
+    try:
+        _lib.call("cse_attention_fwd", _p(q.to(DEV)), nseq, n, prec, _p(out), _st())
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().cse_debug_force_mma_attention(0)
     ref = _attention_ref(q.float(), nseq, n)
     assert rel_l2(out.float().cpu(), ref) < (3e-6 if prec == FP32 else 1e-2)
 

@@ -20,6 +20,7 @@ def main():
     m.add_mt_pipeline()
     m.load_state_dict(sd)
     m = m.cuda().eval()
+    m.use_cuda_graph = len(sys.argv) > 5 and sys.argv[5] == "graph"
     for B, T, prec, iters in cases:
         mix = torch.randn(B, T, device="cuda") * 0.1
         ctx = torch.randn(B, 1, 4096, device="cuda")
