@@ -473,6 +473,13 @@ int cse_linear(const void* A, int lda, const void* W, const float* bias, float b
                           ldc, M, N, K, relu, (cudaStream_t)stream);
 }
 
+int cse_ln_linear(const float* R, const float* gamma, const float* beta, float eps, const void* W_bf16,
+                  const float* bias, void* C, int ldc, int M, int N, int relu, void* stream) {
+  CSE_REQUIRE(R && gamma && beta && W_bf16 && C, "ln_linear: NULL argument");
+  return launch_gemm_ln_tc(R, gamma, beta, eps, (const bf16*)W_bf16, bias, (bf16*)C, ldc, M, N, relu,
+                           (cudaStream_t)stream);
+}
+
 int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps, int act_dtype,
                       void* out, void* stream) {
   CSE_REQUIRE(x && g && b && out, "layernorm_fwd: NULL argument");

@@ -160,6 +160,9 @@ int launch_gemm_simt(const float* A, int lda, const float* W, const float* bias,
 int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, float bias_scale,
                    const float* residual, void* C, int ldc, int M, int N, int K, int relu,
                    int out_fp32, cudaStream_t st);
+// gemm_ln_tc.cu: C(bf16) = act(LN(R) W^T + bias), K = 256
+int launch_gemm_ln_tc(const float* R, const float* gamma, const float* beta, float eps, const bf16* W,
+                      const float* bias, bf16* C, int ldc, int M, int N, int relu, cudaStream_t st);
 // attention.cu
 int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaStream_t st);
 int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_t st);  // attention_tc.cu

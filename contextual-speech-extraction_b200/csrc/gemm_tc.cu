@@ -51,11 +51,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware
+      : "memory");                               // instead of burning issue slots while it polls
   return ok != 0;
 }
 // Bounded wait (~2 s at 2 GHz): a broken pipeline traps with a message instead of hanging.
@@ -172,14 +172,17 @@ struct TcCfg {
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiBufBytes = 32 * 128;  // one chunk: 32 rows x 128 B
   static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;  // double-buffered per warp
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256;
+  static constexpr int kBiasMax = 1024;          // bias[N] staged in shared memory when N <= 1024
+  static constexpr size_t kSmem =
+      1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256 + kBiasMax * 4;
 };
 
 template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
-               float bias_scale, int accumulate_into_c, int M, int N, int K, int relu) {
+               float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
+               int relu) {
   using Cfg = TcCfg<BN>;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
@@ -212,6 +215,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  // bias -> shared memory once per CTA (per-chunk global bias loads were the epilogue's largest
+  // stall in the ncu source view); wider layers fall back to __ldg
+  float* s_bias = reinterpret_cast<float*>(smem_aligned + (sBar + 256 - smem_base));
+  const bool bias_in_smem = bias != nullptr && N <= Cfg::kBiasMax;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < N; i += kGemmThreads) s_bias[i] = bias[i];
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -290,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col_local = half * (BN / 2) + ch * CW;
         const int col0 = n0 + col_local;
         const uint32_t buf = chunk_ctr & 1u;
-        if (chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
+        if (accumulate_into_c && chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
@@ -302,7 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
+              const float4 b4 = bias_in_smem ? *reinterpret_cast<const float4*>(s_bias + col0 + part * 32 + i)
+                                             : __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
               v[i] = fmaf(bias_scale, b4.x, v[i]);
               v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
               v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
@@ -337,15 +347,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t src = stg0 + buf * Cfg::kEpiBufBytes;
-          if (accumulate_into_c)
-            tma_reduce_add_2d(&tmC, src, col0, row_base);
-          else
-            tma_store_2d(&tmC, src, col0, row_base);
-          bulk_commit();
+        if (accumulate_into_c) {
+          // in-place residual update R += tile: TMA reduce-add (the stream is never loaded by the SM)
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, stg0 + buf * Cfg::kEpiBufBytes, col0, row_base);
+            bulk_commit();
+          }
+        } else {
+          // plain output: read the chunk back with lanes along the row (8 lanes x 16 B = one 128-byte
+          // line, 4 rows per instruction) and store directly.  (TMA bulk stores of 4 KB chunks took
+          // ~3 us to release their smem source and capped the epilogue; see profiles/.)
+          __syncwarp();
+          const int c = lane & 7;
+          unsigned char* cbase = reinterpret_cast<unsigned char*>(Cout) +
+                                 ((size_t)col0 * (OUT_F32 ? 4 : 2)) + c * 16;
+          const size_t row_bytes = (size_t)ldc * (OUT_F32 ? 4 : 2);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + (lane >> 3);
+            const uint4 x = stg[rr * 8 + (c ^ (rr & 7))];
+            const int grow = row_base + rr;
+            if (grow < M) *reinterpret_cast<uint4*>(cbase + (size_t)grow * row_bytes) = x;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -407,8 +433,8 @@ struct MapKeyHash {
 
 // Row-major [rows, cols] matrix (bf16 or fp32) with leading dimension ld (elements);
 // box = [box_rows x box_cols] with box_cols * esize == 128 B, SWIZZLE_128B.
-static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                          uint32_t box_cols, uint32_t esize, CUtensorMap* out) {
+int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   uint32_t box_cols, uint32_t esize, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, rows, cols, ld, box_rows, box_cols, esize};
@@ -447,7 +473,7 @@ static int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_
   return 0;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -460,8 +486,8 @@ static int sm_count() {
 
 template <int BN, bool OUT_F32>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                          const float* bias, float bias_scale, int accumulate, int M, int N, int K,
-                          int relu, cudaStream_t st) {
+                          const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
+                          int N, int K, int relu, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -477,7 +503,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int grid = tiles < sm_count() ? tiles : sm_count();
   KernelScope prof(kClsGemmTc, st);
   gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, tmC, bias, bias_scale,
-                                                                      accumulate, M, N, K, relu);
+                                                                      accumulate, C, ldc, M, N, K, relu);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -506,11 +532,11 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
     return 1;
   const int acc = residual != nullptr ? 1 : 0;
   if (BN == 256) {
-    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st);
+    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
   }
-  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st)
-                  : launch_tc_impl<128, false>(tmA, tmB, tmC, bias, bias_scale, acc, M, N, K, relu, st);
+  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                  : launch_tc_impl<128, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
 }
 
 }  // namespace cse

@@ -193,6 +193,13 @@ CSE_API int cse_linear(const void* A, int lda, const void* W, const float* bias,
                        const float* residual, void* C, int ldc, int M, int N, int K,
                        int relu, int out_fp32, int precision, void* stream);
 
+/* Pre-norm sub-block head `norm(src)` -> Linear fused (CSE_transformer.py:385-390 norm1 -> in_proj,
+ * :407-411 norm2 -> ffn.0 + ReLU), CSE_BF16 only: C[M,N] bf16 = act(LN(R[M,256]) W[N,256]^T + bias).
+ * The fp32 residual row is read once; LayerNorm runs in the GEMM's A-operand producer warps. */
+CSE_API int cse_ln_linear(const float* R, const float* gamma, const float* beta, float eps,
+                          const void* W_bf16, const float* bias, void* C, int ldc, int M, int N,
+                          int relu, void* stream);
+
 /* nn.LayerNorm(256, eps) over rows (CSE_transformer.py:358-359,386,408): x [M,256] fp32 -> act. */
 CSE_API int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps,
                               int act_dtype, void* out, void* stream);

@@ -57,6 +57,27 @@ def test_gemm_tc_epilogues(M, N, K):
     assert rel_l2(r.cpu(), exact + bias.double() + res.double()) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,relu", [(1, 128, 0), (128, 768, 0), (517, 1024, 1), (20000, 768, 0),
+                                      (2 * 148 * 128 + 77, 1024, 1), (3 * 148 * 128 + 5, 128, 0)])
+def test_ln_fused_gemm(M, N, relu):
+    """cse_ln_linear: LayerNorm in the A-operand producer == LayerNorm kernel -> bf16 -> GEMM."""
+    R = _rand(M, 256, seed=7) * 2.0 + 0.3
+    g, b = 1 + 0.1 * _rand(256, seed=8), 0.1 * _rand(256, seed=9)
+    W = (_rand(N, 256, seed=10) / 16).to(torch.bfloat16)
+    bias = _rand(N, seed=11)
+    Rd, gd, bd, Wd, biasd = R.to(DEV), g.to(DEV), b.to(DEV), W.to(DEV), bias.to(DEV)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_ln_linear", _lib.ptr(Rd), _lib.ptr(gd), _lib.ptr(bd), 1e-6, _lib.ptr(Wd), _lib.ptr(biasd),
+              _lib.ptr(out), N, M, N, relu, _st())
+    torch.cuda.synchronize()
+    x = R.double()
+    ln = (x - x.mean(-1, keepdim=True)) / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-6) * g.double() + b.double()
+    ref = ln.float().to(torch.bfloat16).double() @ W.double().t() + bias.double()   # same bf16 rounding of A
+    if relu:
+        ref = torch.relu(ref)
+    assert rel_l2(out.float().cpu(), ref) < 5e-3
+
+
 def test_gemm_tc_strided_views():
     """conv2d output [B*L, spk*256] re-read as [B*L*spk, 256] (abi.cu masknet_impl) and lda > K."""
     M, K = 777, 256

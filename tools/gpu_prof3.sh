@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/quick_time.py 16 32000 bf16 1 > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm_ln_tc -s 4 -c 1 -o gpurun_out/prof_ln -f \
+    python tools/quick_time.py 16 32000 bf16 1 > gpurun_out/ncu_ln.log 2>&1
+echo "ncu ln: exit $?"
