@@ -78,6 +78,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast load: the box lands at the same shared-memory offset in every CTA of `mask` and
+// completes `bytes` on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                                  int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
@@ -201,13 +225,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kTM - 1) / kTM, n_tiles = N / BN;
-  const int total_tiles = m_tiles * n_tiles;
   const int num_kb = K / kTK;
+  // CTA pairs (clusters of 2): both CTAs of a pair walk the same n-tile sequence on adjacent
+  // m-tiles, so every weight tile is fetched from L2 ONCE per pair — each CTA loads half of it and
+  // TMA-multicasts that half into both CTAs' shared memory.  (These GEMMs were bound by L2->SM
+  // bandwidth, ~9 TB/s aggregate, because the weights are re-streamed for every 128-row tile.)
+  const int cta_rank = (int)cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_pt = ((m_tiles + 1) >> 1) * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 2);  // released by the MMA issuers of BOTH CTAs of the pair
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -224,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -231,14 +262,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= TMA producer =================
     // The whole warp walks the loop (keeps it convergent for the teardown barrier); lane 0 acts.
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
+    for (int pt = pair_id; pt < total_pt; pt += npairs) {
+      const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
           mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kABytes, &tmA, bar_full + 8 * stage, kb * kTK, m0);
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, bar_full + 8 * stage, kb * kTK, n0);
+          // this CTA's half of the weight tile -> both CTAs (rows past the M tail read as zeros)
+          tma_load_2d_mcast(sB + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / 2), &tmB,
+                            bar_full + 8 * stage, kb * kTK, n0 + cta_rank * (BN / 2), (uint16_t)3);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -248,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
     constexpr uint32_t idesc = make_idesc_bf16(kTM, BN);
     uint32_t stage = 0, phase = 0, astage = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int pt = pair_id; pt < total_pt; pt += npairs) {
       if (lane == 0) {
         mbar_wait(bar_tempty + 8 * astage, aphase ^ 1, 2);
         tc_fence_after();
@@ -266,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
+          umma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);  // release the stage in both CTAs
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -288,8 +321,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stg0 = sEpi + (warp - 2) * 2 * Cfg::kEpiBufBytes;
     unsigned char* stg0_ptr = smem_aligned + (stg0 - smem_base);
     uint32_t astage = 0, aphase = 0, chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * BN;
+    for (int pt = pair_id; pt < total_pt; pt += npairs) {
+      const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
       const int row_base = m0 + quarter * 32;
       mbar_wait(bar_tfull + 8 * astage, aphase, 4);
       tc_fence_after();
@@ -299,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col_local = half * (BN / 2) + ch * CW;
         const int col0 = n0 + col_local;
         const uint32_t buf = chunk_ctr & 1u;
-        if (accumulate_into_c && chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
+        if (chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
@@ -347,31 +380,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (accumulate_into_c) {
-          // in-place residual update R += tile: TMA reduce-add (the stream is never loaded by the SM)
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            tma_reduce_add_2d(&tmC, stg0 + buf * Cfg::kEpiBufBytes, col0, row_base);
-            bulk_commit();
-          }
-        } else {
-          // plain output: read the chunk back with lanes along the row (8 lanes x 16 B = one 128-byte
-          // line, 4 rows per instruction) and store directly.  (TMA bulk stores of 4 KB chunks took
-          // ~3 us to release their smem source and capped the epilogue; see profiles/.)
-          __syncwarp();
-          const int c = lane & 7;
-          unsigned char* cbase = reinterpret_cast<unsigned char*>(Cout) +
-                                 ((size_t)col0 * (OUT_F32 ? 4 : 2)) + c * 16;
-          const size_t row_bytes = (size_t)ldc * (OUT_F32 ? 4 : 2);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int rr = jj * 4 + (lane >> 3);
-            const uint4 x = stg[rr * 8 + (c ^ (rr & 7))];
-            const int grow = row_base + rr;
-            if (grow < M) *reinterpret_cast<uint4*>(cbase + (size_t)grow * row_bytes) = x;
-          }
-          __syncwarp();
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t src = stg0 + buf * Cfg::kEpiBufBytes;
+          if (accumulate_into_c)
+            tma_reduce_add_2d(&tmC, src, col0, row_base);  // in-place residual update R += tile
+          else
+            tma_store_2d(&tmC, src, col0, row_base);
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -385,6 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // neither CTA retires while the peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -499,11 +517,28 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     }
     configured = true;
   }
-  const int tiles = ceil_div(M, kTM) * (N / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int pair_tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN);
+  const int max_pairs = sm_count() / 2;
+  const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  gemm_tc_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmem, st>>>(tmA, tmB, tmC, bias, bias_scale,
-                                                                      accumulate, C, ldc, M, N, K, relu);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OUT_F32>, tmA, tmB, tmC, bias, bias_scale,
+                                      accumulate, C, ldc, M, N, K, relu);
+  if (le != cudaSuccess) {
+    set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return check_launch("gemm_tc_kernel");
 }
 
@@ -527,7 +562,7 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
   const int BN = (N % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB, tmC;
   if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
-  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, kTK, 2, &tmB)) return 1;
+  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(BN / 2), kTK, 2, &tmB)) return 1;  // half tile per CTA
   if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, out_fp32 ? 32 : 64, out_fp32 ? 4 : 2, &tmC))
     return 1;
   const int acc = residual != nullptr ? 1 : 0;

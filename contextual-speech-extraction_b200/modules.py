@@ -255,9 +255,21 @@ class SBTransformerBlock_CSE(nn.Module):
         Bp, n, E = x.shape
         if E != N_CH:
             _unsupported(f"d_model={E}")
-        st = C.c_void_p(current_stream(x.device))
-        dev, adt = x.device, _act_dtype(prec)
+        dev = x.device
+        st = C.c_void_p(current_stream(dev))
         R = (x.float() + self.pos_enc.pe[:, :n]).contiguous()          # residual stream, fp32
+        M = Bp * n
+        self._run_layers(R, Bp, n, prec)
+        out = torch.empty(Bp, n, N_CH, dtype=torch.float32, device=dev)
+        _lib.call("cse_layernorm_fwd", _lib.ptr(R), _lib.ptr(self.mdl.norm.norm.weight),
+                  _lib.ptr(self.mdl.norm.norm.bias), M, 1e-6, FP32, _lib.ptr(out), st)
+        return out
+
+    def _run_layers(self, R, Bp, n, prec):
+        """The 8 pre-norm layers, in place on the fp32 residual stream R [Bp*n, 256] (PE already
+        added; the stack's final LayerNorm is applied by the caller / the stack tail)."""
+        dev, adt = R.device, _act_dtype(prec)
+        st = C.c_void_p(current_stream(dev))
         M = Bp * n
         H = torch.empty(M, N_CH, dtype=adt, device=dev)
         QKV = torch.empty(M, 3 * N_CH, dtype=adt, device=dev)
@@ -280,10 +292,6 @@ class SBTransformerBlock_CSE(nn.Module):
                       _lib.ptr(ffn[0].bias), 1.0, None, _lib.ptr(F1), D_FFN, M, D_FFN, N_CH, 1, 0, prec, st)
             _lib.call("cse_linear", _lib.ptr(F1), D_FFN, _lib.ptr(self._weight(ffn[3].weight, prec)),
                       _lib.ptr(ffn[3].bias), 1.0, _lib.ptr(R), _lib.ptr(R), N_CH, M, N_CH, D_FFN, 0, 1, prec, st)
-        out = torch.empty(Bp, n, N_CH, dtype=torch.float32, device=dev)
-        _lib.call("cse_layernorm_fwd", _lib.ptr(R), _lib.ptr(self.mdl.norm.norm.weight),
-                  _lib.ptr(self.mdl.norm.norm.bias), M, 1e-6, FP32, _lib.ptr(out), st)
-        return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -313,6 +321,55 @@ class Dual_Computation_Block_CSE(nn.Module):
     def add_ctx(self):
         self.intra_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
         self.inter_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
+
+    returns_pred_head = True      # ContSep flavour (ContSep.py:533); ContExt's returns `out` only
+
+    def forward(self, x, ctx=None, precision=None):
+        """ContSep.py:453-533 on its own, through the per-stage C-ABI entry points:
+        x [B,N,K,S], ctx [B,c,4096] | None -> out [B,N,K,S] (, pred_head [B,N])."""
+        self.intra_mdl._check_supported()
+        self.inter_mdl._check_supported()
+        _check_cuda(x, "x")
+        B, N, K, S = x.shape
+        if N != N_CH or K != CHUNK:
+            _unsupported(f"Dual_Computation_Block input [B,{N},{K},S]")
+        prec = resolve_precision(precision)
+        dev = x.device
+        st = C.c_void_p(current_stream(dev))
+        X = x.permute(0, 3, 2, 1).float().contiguous()                 # [B,S,K,N] channels-last
+        c = 0 if ctx is None else ctx.size(1)
+        tok = [None, None]
+        if c:
+            ctx_d = ctx.contiguous().float()
+            for i, mp in enumerate((self.intra_context_mapper, self.inter_context_mapper)):
+                tok[i] = torch.empty(B, c, N_CH, dtype=torch.float32, device=dev)
+                _lib.call("cse_context_map", _lib.ptr(ctx_d), _lib.ptr(mp.weight), _lib.ptr(mp.bias), B * c,
+                          ctx_d.size(2), _lib.ptr(tok[i]), st)
+        part = torch.empty(B, 64, 2, dtype=torch.float32, device=dev)
+        stat = torch.empty(B, 2, dtype=torch.float32, device=dev)
+
+        def stack(mdl, src, inter, norm, skip):
+            n = (S if inter else K) + c
+            nseq = B * (K if inter else S)
+            R = torch.empty(nseq * n, N_CH, dtype=torch.float32, device=dev)
+            _lib.call("cse_build_sequences", _lib.ptr(src), _lib.ptr(tok[inter]), _lib.ptr(mdl.pos_enc.pe), B, S, c,
+                      inter, _lib.ptr(R), st)
+            mdl._run_layers(R, nseq, n, prec)
+            out = torch.empty(B, S, K, N_CH, dtype=torch.float32, device=dev)
+            _lib.call("cse_stack_finish", _lib.ptr(R), _lib.ptr(mdl.mdl.norm.norm.weight),
+                      _lib.ptr(mdl.mdl.norm.norm.bias), _lib.ptr(norm.weight), _lib.ptr(norm.bias), _lib.ptr(skip),
+                      B, S, c, inter, _lib.ptr(out), _lib.ptr(part), _lib.ptr(stat), st)
+            return R, out
+
+        _, intra = stack(self.intra_mdl, X, 0, self.intra_norm, X)               # + x (skip around intra)
+        R_inter, out = stack(self.inter_mdl, intra, 1, self.inter_norm, intra)   # + intra
+        out = out.permute(0, 3, 2, 1)                                             # [B,N,K,S] view
+        if not self.returns_pred_head:
+            return out
+        pred = torch.empty(B, N_CH, dtype=torch.float32, device=dev)
+        _lib.call("cse_pred_head", _lib.ptr(R_inter), _lib.ptr(self.inter_mdl.mdl.norm.norm.weight),
+                  _lib.ptr(self.inter_mdl.mdl.norm.norm.bias), B, S, c, _lib.ptr(pred), st)
+        return out, pred
 
 
 class Dual_Path_Model_CSE(nn.Module):
@@ -413,9 +470,15 @@ class Dual_Path_Model(Dual_Path_Model_CSE):
 
 
 class Dual_Path_Model_CSE_Ext(Dual_Path_Model_CSE):
-    """ContExt.py:132-294 flavour: forward returns the mask only."""
+    """ContExt.py:132-294 flavour: forward returns the mask only (and so do its blocks,
+    ContExt.py:557)."""
 
     returns_pred_head = False
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        for blk in self.dual_mdl:
+            blk.returns_pred_head = False
 
 
 # ----------------------------------------------------------------------------------------------

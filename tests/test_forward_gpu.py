@@ -207,6 +207,25 @@ def test_submodule_api_shapes_and_values():
         assert rel_l2(y16.cpu(), ref) < 3e-2
 
 
+def test_dual_computation_block_alone():
+    """Dual_Computation_Block_CSE.forward(x [B,N,K,S], ctx) used on its own (ContSep.py:453-533)."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_b2_t4000")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 256, 250, 5, generator=g)
+    with torch.no_grad():
+        ref_out, ref_ph = O.dual_block(sd, 1, x, ctx)
+        out, ph = m.masknet.dual_mdl[1](x.to(DEV), ctx.to(DEV), precision="fp32")
+        out0, _ = m.masknet.dual_mdl[0](x.to(DEV), None, precision="fp32")            # c = 0
+        ref0, _ = O.dual_block(sd, 0, x, None)
+    assert out.shape == ref_out.shape == (2, 256, 250, 5)
+    assert rel_l2(out.cpu(), ref_out) < FP32_TOL
+    assert rel_l2(ph.cpu(), ref_ph) < FP32_TOL
+    assert rel_l2(out0.cpu(), ref0) < FP32_TOL
+
+
 def test_errors_are_python_exceptions():
     m = PlainSepformer(2).to(DEV).eval()
     with pytest.raises(RuntimeError):
