@@ -58,6 +58,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");                               // instead of burning issue slots while it polls
   return ok != 0;
 }
+// Latency-critical single-thread roles (TMA producer, MMA issuer) poll WITHOUT the suspend hint:
+// a sleeping thread wakes late and every handoff in the load -> MMA -> release ring pays for it.
+__device__ __forceinline__ bool mbar_try_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_spin(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_spin(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("gemm_tc: mbarrier timeout (tag %d, block %d, thread %d, parity %u)\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait (~2 s at 2 GHz): a broken pipeline traps with a message instead of hanging.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
@@ -188,17 +212,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 3 : 4;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kTK * 2;   // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiBufBytes = 32 * 128;  // one chunk: 32 rows x 128 B
-  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;  // double-buffered per warp
-  static constexpr int kBiasMax = 1024;          // bias[N] staged in shared memory when N <= 1024
-  static constexpr size_t kSmem =
-      1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256 + kBiasMax * 4;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufBytes;  // one staging chunk per warp
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256;
 };
 
 template <int BN, bool OUT_F32>
@@ -245,12 +267,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // bias -> shared memory once per CTA (per-chunk global bias loads were the epilogue's largest
-  // stall in the ncu source view); wider layers fall back to __ldg
-  float* s_bias = reinterpret_cast<float*>(smem_aligned + (sBar + 256 - smem_base));
-  const bool bias_in_smem = bias != nullptr && N <= Cfg::kBiasMax;
-  if (bias_in_smem)
-    for (int i = threadIdx.x; i < N; i += kGemmThreads) s_bias[i] = bias[i];
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -266,7 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
+          mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
           mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kABytes, &tmA, bar_full + 8 * stage, kb * kTK, m0);
           // this CTA's half of the weight tile -> both CTAs (rows past the M tail read as zeros)
@@ -283,14 +299,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0, astage = 0, aphase = 0;
     for (int pt = pair_id; pt < total_pt; pt += npairs) {
       if (lane == 0) {
-        mbar_wait(bar_tempty + 8 * astage, aphase ^ 1, 2);
+        mbar_wait_spin(bar_tempty + 8 * astage, aphase ^ 1, 2);
         tc_fence_after();
       }
       __syncwarp();
       const uint32_t d_tmem = tmem_base + astage * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
-          mbar_wait(bar_full + 8 * stage, phase, 3);
+          mbar_wait_spin(bar_full + 8 * stage, phase, 3);
           tc_fence_after();
           const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::kABytes);
           const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
@@ -318,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCH = (BN / 2) / CW;
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    const uint32_t stg0 = sEpi + (warp - 2) * 2 * Cfg::kEpiBufBytes;
+    const uint32_t stg0 = sEpi + (warp - 2) * Cfg::kEpiBufBytes;
     unsigned char* stg0_ptr = smem_aligned + (stg0 - smem_base);
     uint32_t astage = 0, aphase = 0, chunk_ctr = 0;
     for (int pt = pair_id; pt < total_pt; pt += npairs) {
@@ -331,9 +347,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ch = 0; ch < NCH; ++ch, ++chunk_ctr) {
         const int col_local = half * (BN / 2) + ch * CW;
         const int col0 = n0 + col_local;
-        const uint32_t buf = chunk_ctr & 1u;
-        if (chunk_ctr >= 2) {  // the TMA that read this buffer two chunks ago must have drained it
-          if (lane == 0) bulk_wait_read<1>();
+        const uint32_t buf = 0;
+        if (chunk_ctr >= 1) {  // the TMA store of the previous chunk must have drained the staging tile
+          if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
         }
         uint4* stg = reinterpret_cast<uint4*>(stg0_ptr + buf * Cfg::kEpiBufBytes);
@@ -344,8 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = bias_in_smem ? *reinterpret_cast<const float4*>(s_bias + col0 + part * 32 + i)
-                                             : __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
               v[i] = fmaf(bias_scale, b4.x, v[i]);
               v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
               v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
@@ -384,10 +399,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) {
           const uint32_t src = stg0 + buf * Cfg::kEpiBufBytes;
-          if (accumulate_into_c)
-            tma_reduce_add_2d(&tmC, src, col0, row_base);  // in-place residual update R += tile
-          else
-            tma_store_2d(&tmC, src, col0, row_base);
+          // in-place residual update R += tile: TMA reduce-add (the stream is never loaded by the SM);
+          // plain outputs: TMA store. (Direct coalesced st.global from the staging tile was measured
+          // slower: QKV 75 vs 63 us.)
+          if (accumulate_into_c) tma_reduce_add_2d(&tmC, src, col0, row_base);
+          else tma_store_2d(&tmC, src, col0, row_base);
           bulk_commit();
         }
       }
