@@ -19,17 +19,33 @@
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cse {
 
 constexpr int kTM = 128;  // UMMA M
 constexpr int kTK = 64;   // K per stage: 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;  // producer + MMA + 8 epilogue warps
+#ifndef CSE_EPI_WARPS
+#define CSE_EPI_WARPS 8
+#endif
+#ifndef CSE_STAGES_256
+#define CSE_STAGES_256 4
+#endif
+#ifndef CSE_EPI_ROW_BYTES
+#define CSE_EPI_ROW_BYTES 128  // bytes per row of one epilogue staging chunk: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+#endif
+#ifndef CSE_PAIR_STAGES
+#define CSE_PAIR_STAGES 5
+#endif
+#ifndef CSE_PAIR_EPIBUFS
+#define CSE_PAIR_EPIBUFS 2
+#endif
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -118,6 +134,47 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
+// ---- CTA-pair mode (cta_group::2): one UMMA spans the two SMs of a cluster ----
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on an mbarrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
+               "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
@@ -189,6 +246,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
 // bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1)
 // | [32,46) SBO>>4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2.
@@ -210,38 +279,56 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int BN>
+// PAIR = one 256 x BN UMMA (cta_group::2) per CTA pair: each CTA stages its own 128 A rows and only
+// HALF of the weight tile, so a stage is 32 KB instead of 48 KB and the shared memory this frees
+// goes to a deeper load ring and a second epilogue staging chunk per warp.
+// ARES (K == 256 with several n-tiles: QKV, FFN1) = the 128 x 256 A tile stays RESIDENT in shared memory
+// (4 k-blocks, 64 KB) while the CTA walks the n-tiles of its rows, so A crosses the L2 once per row tile
+// instead of once per (row tile, n-tile); the ring stages then hold weight tiles only.  These GEMMs are
+// bound by L2 throughput (~10 TB/s for operand loads + output stores together), not by HBM or the MMAs.
+template <int BN, bool PAIR, bool ARES = false>
 struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = PAIR ? CSE_PAIR_STAGES : ((BN == 256) ? CSE_STAGES_256 : 6);
   static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * kTK * 2;   // 32 KB / 16 KB
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kTK * 2;
+  static constexpr int kAStages = ARES ? 4 : kStages;  // ARES: one slot per k-block of the resident tile
+  static constexpr int kStageBytes = kABytes + kBBytes;   // bytes one k-block brings in (A + W)
   static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
-  static constexpr int kEpiWarps = 8;
-  static constexpr int kEpiBufBytes = 32 * 128;  // one chunk: 32 rows x 128 B
-  static constexpr int kEpiBytes = kEpiWarps * kEpiBufBytes;  // one staging chunk per warp
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiBytes + 256;
+  static constexpr int kEpiWarps = (BN == 256) ? CSE_EPI_WARPS : 8;  // 4 TMEM lane quarters x column groups
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;              // producer + MMA + epilogue warps
+  // 4 KB of staging per epilogue warp, cut into chunks of 32 rows x kRowBytes.  With 64-byte rows a warp
+  // has TWO chunks, so the TMA store of one chunk drains while the next is being converted (a 4 KB
+  // store takes ~0.8 us to release its source when the write path is busy, as long as the conversion).
+  static constexpr int kRowBytes = CSE_EPI_ROW_BYTES;
+  static constexpr int kEpiBufs = (PAIR ? CSE_PAIR_EPIBUFS : 1) * (128 / kRowBytes);
+  static constexpr int kEpiBufBytes = 32 * kRowBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
+  static constexpr int kRingBytes = kAStages * kABytes + kStages * kBBytes;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kRingBytes + kEpiBytes + 384;
 };
 
-template <int BN, bool OUT_F32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool OUT_F32, bool PAIR, bool ARES>
+__global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
                int relu) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR, ARES>;
+  static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + Cfg::kStages * Cfg::kABytes;
-  const uint32_t sEpi = smem_base + Cfg::kStages * Cfg::kStageBytes;  // multiple of 1024
+  const uint32_t sB = smem_base + Cfg::kAStages * Cfg::kABytes;
+  const uint32_t sEpi = smem_base + Cfg::kRingBytes;  // multiple of 1024
   const uint32_t sBar = sEpi + Cfg::kEpiBytes;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
   const uint32_t bar_full = sBar;
   const uint32_t bar_empty = sBar + 8 * Cfg::kStages;
   const uint32_t bar_tfull = sBar + 16 * Cfg::kStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_afull = bar_tempty + 16;   // ARES: [4] resident-A k-block landed
+  const uint32_t bar_aempty = bar_afull + 32;   // ARES: [4] resident-A k-block no longer read by any MMA
+  const uint32_t tmem_slot = bar_aempty + 32;
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
@@ -255,19 +342,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int cta_rank = (int)cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int total_pt = ((m_tiles + 1) >> 1) * n_tiles;
+  // Tile walk.  Default: pair p takes tiles p, p + npairs, ... (n fastest, so the pairs that share an
+  // A tile run at the same time).  ARES: pair p takes a CONTIGUOUS run of tiles, so consecutive tiles
+  // share their row tile and A is (re)loaded only when the row tile changes.
+  const int t_begin = ARES ? (int)((long long)pair_id * total_pt / npairs) : pair_id;
+  const int t_end = ARES ? (int)((long long)(pair_id + 1) * total_pt / npairs) : total_pt;
+  const int t_step = ARES ? 1 : npairs;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 2);  // released by the MMA issuers of BOTH CTAs of the pair
+      mbar_init(bar_empty + 8 * s, PAIR ? 1 : 2);  // !PAIR: released by the MMA issuers of BOTH CTAs
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps);  // one arrive per epilogue warp
+      // one arrive per epilogue warp; PAIR: the leader's barrier collects both CTAs' warps
+      mbar_init(bar_tempty + 8 * s, PAIR ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);  // same warp id in both CTAs
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
@@ -277,11 +378,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA producer =================
     // The whole warp walks the loop (keeps it convergent for the teardown barrier); lane 0 acts.
-    uint32_t stage = 0, phase = 0;
-    for (int pt = pair_id; pt < total_pt; pt += npairs) {
+    uint32_t stage = 0, phase = 0, seg = 0;
+    for (int pt = t_begin; pt < t_end; pt += t_step) {
       const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
+      const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (lane == 0) {
+        if constexpr (ARES) {
+          if (lane == 0) {
+            if (new_rows) {  // k-block kb of the previous row tile has been consumed by its last MMA
+              mbar_wait_spin(bar_aempty + 8 * kb, (seg & 1u) ^ 1u, 5);
+              mbar_expect_tx(bar_afull + 8 * kb, Cfg::kABytes);
+              tma_load_2d(sA + kb * Cfg::kABytes, &tmA, bar_afull + 8 * kb, kb * kTK, m0);
+            }
+            mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
+            mbar_expect_tx(bar_full + 8 * stage, Cfg::kBBytes);
+            tma_load_2d_mcast(sB + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / 2), &tmB,
+                              bar_full + 8 * stage, kb * kTK, n0 + cta_rank * (BN / 2), (uint16_t)3);
+          }
+        } else if constexpr (PAIR) {
+          if (lane == 0) {
+            mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);  // the pair's UMMAs have consumed this stage
+            // all four boxes of the pair (2 x A rows, 2 x W halves) complete on the LEADER's barrier
+            const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
+            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sA + stage * Cfg::kABytes, &tmA, lead_full, kb * kTK, m0);
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, lead_full, kb * kTK, n0 + cta_rank * (BN / 2));
+          }
+        } else if (lane == 0) {
           mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
           mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kABytes, &tmA, bar_full + 8 * stage, kb * kTK, m0);
@@ -292,12 +415,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (new_rows) ++seg;
     }
   } else if (warp == 1) {
     // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
-    constexpr uint32_t idesc = make_idesc_bf16(kTM, BN);
-    uint32_t stage = 0, phase = 0, astage = 0, aphase = 0;
-    for (int pt = pair_id; pt < total_pt; pt += npairs) {
+    // PAIR: only the leader CTA issues; each UMMA is 256 x BN x 16 across both SMs (A rows and the
+    // weight halves come from the same shared-memory offsets in both CTAs, D lands in both TMEMs).
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
+    uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, seg = 0;
+    for (int pt = t_begin; pt < t_end && (!PAIR || cta_rank == 0); pt += t_step) {
+      const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
+      const bool last_use = ARES && (pt + 1 == t_end || (pt + 1) % n_tiles == 0);
+      if (new_rows && pt != t_begin) ++seg;
       if (lane == 0) {
         mbar_wait_spin(bar_tempty + 8 * astage, aphase ^ 1, 2);
         tc_fence_after();
@@ -306,21 +435,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t d_tmem = tmem_base + astage * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
+          if (new_rows) mbar_wait_spin(bar_afull + 8 * kb, seg & 1u, 6);
           mbar_wait_spin(bar_full + 8 * stage, phase, 3);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::kABytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
           const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kTK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#ifndef CSE_DBG_NOMMA
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#endif
           }
-          umma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);  // release the stage in both CTAs
+          // release the stage in both CTAs
+          if constexpr (PAIR) umma_commit_pair_mcast(bar_empty + 8 * stage, (uint16_t)3);
+          else umma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
+          if (last_use) umma_commit(bar_aempty + 8 * kb);  // resident A k-block free for the next row tile
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(bar_tfull + 8 * astage);  // accumulator complete -> epilogue
+      if (lane == 0) {  // accumulator complete -> epilogue (PAIR: of both CTAs)
+        if constexpr (PAIR) umma_commit_pair_mcast(bar_tfull + 8 * astage, (uint16_t)3);
+        else umma_commit(bar_tfull + 8 * astage);
+      }
       __syncwarp();
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
@@ -330,70 +469,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Per chunk: TMEM -> registers (one output row per thread) -> bias/ReLU/pack -> warp-private
     // SWIZZLE_128B staging tile -> one elected lane issues a TMA store (or reduce-add).  Two
     // staging buffers per warp: the store of chunk i overlaps the TMEM load of chunk i+1.
-    constexpr int CW = OUT_F32 ? 32 : 64;        // columns per chunk = 128 B per row
-    constexpr int NCH = (BN / 2) / CW;
+    constexpr int CW = Cfg::kRowBytes / (OUT_F32 ? 4 : 2);  // columns per chunk
+    constexpr int GW = BN / (Cfg::kEpiWarps / 4);  // columns per warp
+    constexpr int NCH = GW / CW;
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const uint32_t stg0 = sEpi + (warp - 2) * Cfg::kEpiBufBytes;
+    const int cgroup = (warp - 2) >> 2;
+    const uint32_t stg0 = sEpi + (warp - 2) * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
     unsigned char* stg0_ptr = smem_aligned + (stg0 - smem_base);
     uint32_t astage = 0, aphase = 0, chunk_ctr = 0;
-    for (int pt = pair_id; pt < total_pt; pt += npairs) {
+    float bv[CW];  // bias_scale * bias of the upcoming chunk (lane-uniform), prefetched one chunk ahead
+    auto load_bias = [&](int col) {
+#pragma unroll
+      for (int i = 0; i < CW; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + i));
+        bv[i] = bias_scale * b4.x;
+        bv[i + 1] = bias_scale * b4.y;
+        bv[i + 2] = bias_scale * b4.z;
+        bv[i + 3] = bias_scale * b4.w;
+      }
+    };
+    if (bias != nullptr && t_begin < t_end) load_bias((t_begin % n_tiles) * BN + cgroup * GW);
+    for (int pt = t_begin; pt < t_end; pt += t_step) {
       const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
       const int row_base = m0 + quarter * 32;
       mbar_wait(bar_tfull + 8 * astage, aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + astage * BN;
+#ifdef CSE_DBG_NOEPI
+      constexpr int kNch = 0;
+#else
+      constexpr int kNch = NCH;
+#endif
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch, ++chunk_ctr) {
-        const int col_local = half * (BN / 2) + ch * CW;
+      for (int ch = 0; ch < kNch; ++ch, ++chunk_ctr) {
+        const int col_local = cgroup * GW + ch * CW;
         const int col0 = n0 + col_local;
-        const uint32_t buf = 0;
-        if (chunk_ctr >= 1) {  // the TMA store of the previous chunk must have drained the staging tile
-          if (lane == 0) bulk_wait_read<0>();
+        const uint32_t buf = chunk_ctr % Cfg::kEpiBufs;
+        if (chunk_ctr >= (uint32_t)Cfg::kEpiBufs) {  // the TMA store that last used this staging tile has drained it
+          if (lane == 0) bulk_wait_read<Cfg::kEpiBufs - 1>();
           __syncwarp();
         }
         uint4* stg = reinterpret_cast<uint4*>(stg0_ptr + buf * Cfg::kEpiBufBytes);
+        float v[CW];
+        if constexpr (CW == 64) tc::tmem_ld64(t_row + col_local, v);
+        else if constexpr (CW == 32) tmem_ld32(t_row + col_local, v);
+        else tmem_ld16(t_row + col_local, v);
+        if (bias != nullptr) {
 #pragma unroll
-        for (int part = 0; part < CW / 32; ++part) {
-          float v[32];
-          tmem_ld32(t_row + col_local + part * 32, v);
-          if (bias != nullptr) {
+          for (int i = 0; i < CW; ++i) v[i] += bv[i];
+          // prefetch the bias of the chunk this warp handles next (this tile's next chunk, or the first
+          // chunk of its next tile): the load latency hides behind the pack/store and the next wait
+          const int npt = pt + t_step;
+          load_bias(ch + 1 < kNch ? col0 + CW : (npt < t_end ? (npt % n_tiles) * BN : n0) + cgroup * GW);
+        }
+        if (relu) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + part * 32 + i));
-              v[i] = fmaf(bias_scale, b4.x, v[i]);
-              v[i + 1] = fmaf(bias_scale, b4.y, v[i + 1]);
-              v[i + 2] = fmaf(bias_scale, b4.z, v[i + 2]);
-              v[i + 3] = fmaf(bias_scale, b4.w, v[i + 3]);
-            }
-          }
-          if (relu) {
+          for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        // row = lane; 16-byte slot index XOR-swizzled exactly as the TMA box expects
+        // (SWIZZLE_128B: slot ^ (row & 7); SWIZZLE_64B: slot ^ ((row >> 1) & 3)) -> conflict-free STS.128
+        constexpr int kSlots = Cfg::kRowBytes / 16;
+        const int sw = (kSlots == 8) ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          // row = lane; 16-byte chunk index XOR (row & 7) == the TMA SWIZZLE_128B pattern
+        for (int i = 0; i < kSlots; ++i) {
+          uint4 u;
           if constexpr (OUT_F32) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4 u;
-              u.x = __float_as_uint(v[4 * i]);
-              u.y = __float_as_uint(v[4 * i + 1]);
-              u.z = __float_as_uint(v[4 * i + 2]);
-              u.w = __float_as_uint(v[4 * i + 3]);
-              stg[lane * 8 + (i ^ (lane & 7))] = u;
-            }
+            u.x = __float_as_uint(v[4 * i]);
+            u.y = __float_as_uint(v[4 * i + 1]);
+            u.z = __float_as_uint(v[4 * i + 2]);
+            u.w = __float_as_uint(v[4 * i + 3]);
           } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-              h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              stg[lane * 8 + ((part * 4 + i) ^ (lane & 7))] = u;
-            }
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+            h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+            h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+            h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
           }
+          stg[lane * kSlots + (i ^ sw)] = u;
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -402,14 +554,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // in-place residual update R += tile: TMA reduce-add (the stream is never loaded by the SM);
           // plain outputs: TMA store. (Direct coalesced st.global from the staging tile was measured
           // slower: QKV 75 vs 63 us.)
+#ifndef CSE_DBG_NOSTORE
           if (accumulate_into_c) tma_reduce_add_2d(&tmC, src, col0, row_base);
           else tma_store_2d(&tmC, src, col0, row_base);
           bulk_commit();
+#else
+          (void)src;
+#endif
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * astage);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * astage, 0));
+        else mbar_arrive(bar_tempty + 8 * astage);
+      }
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();  // all output writes complete before the CTA retires
@@ -421,7 +580,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   cluster_sync_all();  // neither CTA retires while the peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -466,7 +626,7 @@ struct MapKeyHash {
 };
 
 // Row-major [rows, cols] matrix (bf16 or fp32) with leading dimension ld (elements);
-// box = [box_rows x box_cols] with box_cols * esize == 128 B, SWIZZLE_128B.
+// box = [box_rows x box_cols] with box_cols * esize == 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B).
 int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                    uint32_t box_cols, uint32_t esize, CUtensorMap* out) {
   static std::mutex mu;
@@ -491,7 +651,8 @@ int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, u
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   box_cols * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u esize=%u",
@@ -518,14 +679,14 @@ int sm_count() {
   return n;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, bool PAIR, bool ARES = false>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
                           int N, int K, int relu, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR, ARES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
@@ -539,7 +700,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   KernelScope prof(kClsGemmTc, st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -549,7 +710,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OUT_F32>, tmA, tmB, tmC, bias, bias_scale,
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>, tmA, tmB, tmC, bias, bias_scale,
                                       accumulate, C, ldc, M, N, K, relu);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
@@ -579,15 +740,32 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
   CUtensorMap tmA, tmB, tmC;
   if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
   if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(BN / 2), kTK, 2, &tmB)) return 1;  // half tile per CTA
-  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, out_fp32 ? 32 : 64, out_fp32 ? 4 : 2, &tmC))
+  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CSE_EPI_ROW_BYTES / (out_fp32 ? 4 : 2),
+                     out_fp32 ? 4 : 2, &tmC))
     return 1;
   const int acc = residual != nullptr ? 1 : 0;
-  if (BN == 256) {
-    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+  static const bool pair_mma = []() {  // CSE_GEMM_PAIR=0 selects the per-CTA UMMA + multicast variant (A/B aid)
+    const char* e = getenv("CSE_GEMM_PAIR");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (BN == 256 && pair_mma) {
+    return out_fp32 ? launch_tc_impl<256, true, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
   }
-  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                  : launch_tc_impl<128, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+  static const bool a_resident = []() {  // CSE_GEMM_ARES=1 selects the resident-A variant (measured slower: A/B aid)
+    const char* e = getenv("CSE_GEMM_ARES");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (BN == 256 && K == 4 * kTK && N > BN && a_resident) {
+    return out_fp32 ? launch_tc_impl<256, true, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+  }
+  if (BN == 256) {
+    return out_fp32 ? launch_tc_impl<256, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+  }
+  return out_fp32 ? launch_tc_impl<128, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                  : launch_tc_impl<128, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
 }
 
 }  // namespace cse

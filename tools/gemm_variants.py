@@ -1,0 +1,81 @@
+"""Development aid: build gemm_tc.cu variants (-D flags) into tools/_variants/ and time the four
+per-layer GEMM shapes of cfg2 through the C ABI (cse_linear).  Not part of the product or the bench.
+
+  python tools/gemm_variants.py build            # here (nvcc cross-compiles)
+  python tools/gemm_variants.py run [name ...]   # on the GPU box
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "contextual-speech-extraction_b200", "csrc")
+OUT = os.path.join(ROOT, "tools", "_variants")
+NVCC = "/usr/local/cuda/bin/nvcc"
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-fvisibility=hidden"]
+
+BASE = ["-DCSE_EPI_WARPS=8", "-DCSE_STAGES_256=4", "-DCSE_PAIR_STAGES=5", "-DCSE_PAIR_EPIBUFS=2"]
+VARIANTS = {
+    "r128": BASE + ["-DCSE_EPI_ROW_BYTES=128"],
+    "r64": BASE + ["-DCSE_EPI_ROW_BYTES=64"],
+    "r64_nostore": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOSTORE"],
+    "r64_noepi": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOEPI"],
+    "r64_nomma": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOMMA"],
+}
+
+
+def build(names):
+    os.makedirs(OUT, exist_ok=True)
+    others = [o for o in glob.glob(os.path.join(CSRC, "*.o")) if not o.endswith("gemm_tc.o")]
+    for name in names or VARIANTS:
+        obj = os.path.join(OUT, f"gemm_tc_{name}.o")
+        subprocess.check_call([NVCC] + FLAGS + VARIANTS[name] + ["-c", os.path.join(CSRC, "gemm_tc.cu"), "-o", obj])
+        lib = os.path.join(OUT, f"libcse_{name}.so")
+        subprocess.check_call([NVCC, "-shared", "-o", lib, obj] + others + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        print("built", lib)
+
+
+def run(names):
+    import torch
+    M = 136544
+    shapes = [("qkv ", 768, 256, 0, 0), ("outp", 256, 256, 0, 1), ("ffn1", 1024, 256, 1, 0), ("ffn2", 256, 1024, 0, 1)]
+    torch.manual_seed(0)
+    for name in names or sorted(n[7:-3] for n in os.listdir(OUT) if n.startswith('libcse_')):
+        lib = C.CDLL(os.path.join(OUT, f"libcse_{name}.so"))
+        lib.cse_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.cse_last_error.restype = C.c_char_p
+        line = [f"{name:12s} pair={os.environ.get('CSE_GEMM_PAIR', '0')} ares={os.environ.get('CSE_GEMM_ARES', '0')}"]
+        for tag, N, K, relu, resid in shapes:
+            A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+            W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+            b = torch.randn(N, device="cuda")
+            out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if resid else torch.bfloat16)
+            st = torch.cuda.current_stream().cuda_stream
+
+            def call(bias=True):
+                rc = lib.cse_linear(A.data_ptr(), K, W.data_ptr(), b.data_ptr() if bias else None, 1.0,
+                                    out.data_ptr() if resid else None, out.data_ptr(), N, M, N, K, relu, resid, 1, st)
+                if rc:
+                    raise RuntimeError(lib.cse_last_error().decode())
+            res = []
+            for bias in (True, False):
+                for _ in range(3):
+                    call(bias)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    call(bias)
+                e1.record()
+                torch.cuda.synchronize()
+                res.append(e0.elapsed_time(e1) / 20 * 1e3)
+            line.append(f"{tag} {res[0]:6.1f}/{res[1]:6.1f}")
+        print("  ".join(line) + "   (us with bias / without)", flush=True)
+
+
+if __name__ == "__main__":
+    (build if sys.argv[1] == "build" else run)(sys.argv[2:])
