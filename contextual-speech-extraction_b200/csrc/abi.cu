@@ -6,6 +6,7 @@
 // caller's stream.  No allocation, no synchronisation (except cse_forward_host), no global state
 // besides the TMA descriptor cache in gemm_tc.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -174,6 +175,15 @@ static int linear(const Plan& pl, const void* A, int lda, const float* W32, cons
                           N, K, relu, st);
 }
 
+// CSE_FFN_FUSED=0 keeps the two-GEMM feed-forward path (A/B aid; the fused kernel is the default)
+static bool ffn_fused_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_FFN_FUSED");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 // SBTransformerBlock_CSE body after the PE add: 8 pre-norm layers on the fp32 residual stream R
 // (TransformerEncoderLayer.forward, CSE_transformer.py:385-416).  The final LayerNorm belongs to
 // the stack tail (stack_finish / pred_head).
@@ -194,6 +204,13 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
     if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
                0, 1, st)) return 1;
     if (launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+    if (pl.precision == CSE_BF16 && ffn_fused_enabled()) {
+      // Linear -> ReLU -> Linear -> residual add in one kernel: the [M,1024] hidden never leaves the SM
+      CSE_REQUIRE(lp.ffn1_w_bf16 && lp.ffn2_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
+      if (launch_ffn_tc((const bf16*)H, (const bf16*)lp.ffn1_w_bf16, lp.ffn1_b, (const bf16*)lp.ffn2_w_bf16,
+                        lp.ffn2_b, R, M, st)) return 1;
+      continue;
+    }
     if (linear(pl, H, kN, lp.ffn1_w, lp.ffn1_w_bf16, lp.ffn1_b, 1.f, nullptr, F1, kFfn, M, kFfn, kN, 1,
                0, st)) return 1;
     if (linear(pl, F1, kFfn, lp.ffn2_w, lp.ffn2_w_bf16, lp.ffn2_b, 1.f, R, R, kN, M, kN, kFfn, 0, 1,
@@ -478,6 +495,13 @@ int cse_ln_linear(const float* R, const float* gamma, const float* beta, float e
   CSE_REQUIRE(R && gamma && beta && W_bf16 && C, "ln_linear: NULL argument");
   return launch_gemm_ln_tc(R, gamma, beta, eps, (const bf16*)W_bf16, bias, (bf16*)C, ldc, M, N, relu,
                            (cudaStream_t)stream);
+}
+
+int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                  const float* b2, float* R, int M, void* stream) {
+  CSE_REQUIRE(A_bf16 && W1_bf16 && b1 && W2_bf16 && b2 && R, "ffn_fused: NULL argument");
+  return launch_ffn_tc((const bf16*)A_bf16, (const bf16*)W1_bf16, b1, (const bf16*)W2_bf16, b2, R, M,
+                       (cudaStream_t)stream);
 }
 
 int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps, int act_dtype,

@@ -161,6 +161,8 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
                    const float* residual, void* C, int ldc, int M, int N, int K, int relu,
                    int out_fp32, cudaStream_t st);
 // gemm_ln_tc.cu: C(bf16) = act(LN(R) W^T + bias), K = 256
+int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float* R,
+                  int M, cudaStream_t st);
 int launch_gemm_ln_tc(const float* R, const float* gamma, const float* beta, float eps, const bf16* W,
                       const float* bias, bf16* C, int ldc, int M, int N, int relu, cudaStream_t st);
 // attention.cu

@@ -193,6 +193,13 @@ CSE_API int cse_linear(const void* A, int lda, const void* W, const float* bias,
                        const float* residual, void* C, int ldc, int M, int N, int K,
                        int relu, int out_fp32, int precision, void* stream);
 
+/* Position-wise feed-forward sub-block with its residual add, fused (CSE_transformer.py:407-411,
+ * PositionalwiseFeedForward :547-566), CSE_BF16 only, d_model 256 / d_ffn 1024:
+ *   R[M,256] (fp32, in place) += relu(A[M,256] W1[1024,256]^T + b1) W2[256,1024]^T + b2
+ * A = norm2 output (bf16), W1/W2 bf16.  The hidden activation stays on chip (TMEM -> smem). */
+CSE_API int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                          const float* b2, float* R, int M, void* stream);
+
 /* Pre-norm sub-block head `norm(src)` -> Linear fused (CSE_transformer.py:385-390 norm1 -> in_proj,
  * :407-411 norm2 -> ffn.0 + ReLU), CSE_BF16 only: C[M,N] bf16 = act(LN(R[M,256]) W[N,256]^T + bias).
  * The fp32 residual row is read once; LayerNorm runs in the GEMM's A-operand producer warps. */

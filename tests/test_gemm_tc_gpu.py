@@ -78,6 +78,36 @@ def test_ln_fused_gemm(M, N, relu):
     assert rel_l2(out.float().cpu(), ref) < 5e-3
 
 
+@pytest.mark.parametrize("M", [1, 128, 129, 517, 20000, 2 * 148 * 128 + 77, 3 * 148 * 128 + 5])
+def test_ffn_fused(M):
+    """cse_ffn_fused == Linear(256,1024) -> ReLU -> bf16 -> Linear(1024,256) -> residual add
+    (PositionalwiseFeedForward + `src = src + ...`, CSE_transformer.py:407-411,547-566)."""
+    A = (_rand(M, 256, seed=21)).to(torch.bfloat16)
+    W1 = (_rand(1024, 256, seed=22) / 16).to(torch.bfloat16)
+    W2 = (_rand(256, 1024, seed=23) / 32).to(torch.bfloat16)
+    b1, b2 = _rand(1024, seed=24), _rand(256, seed=25)
+    R0 = _rand(M, 256, seed=26)
+    Ad, W1d, W2d, b1d, b2d = A.to(DEV), W1.to(DEV), W2.to(DEV), b1.to(DEV), b2.to(DEV)
+    Rd = R0.to(DEV).clone()
+    _lib.call("cse_ffn_fused", _lib.ptr(Ad), _lib.ptr(W1d), _lib.ptr(b1d), _lib.ptr(W2d), _lib.ptr(b2d),
+              _lib.ptr(Rd), M, _st())
+    torch.cuda.synchronize()
+    hid = torch.relu(A.double() @ W1.double().t() + b1.double()).float().to(torch.bfloat16).double()  # same rounding
+    ref = R0.double() + hid @ W2.double().t() + b2.double()
+    # 5e-5: a hidden value that lands within fp32-accumulation error of a bf16 rounding boundary may round
+    # the other way than the float64 reference (one bf16 ulp on that element)
+    assert rel_l2(Rd.cpu(), ref) < 5e-5
+    # and against the two-GEMM path of the same library (bit-level differences only from accumulation order)
+    F1 = torch.empty(M, 1024, dtype=torch.bfloat16, device=DEV)
+    R2 = R0.to(DEV).clone()
+    _lib.call("cse_linear", _lib.ptr(Ad), 256, _lib.ptr(W1d), _lib.ptr(b1d), 1.0, None, _lib.ptr(F1), 1024, M, 1024,
+              256, 1, 0, BF16, _st())
+    _lib.call("cse_linear", _lib.ptr(F1), 1024, _lib.ptr(W2d), _lib.ptr(b2d), 1.0, _lib.ptr(R2), _lib.ptr(R2), 256, M,
+              256, 1024, 0, 1, BF16, _st())
+    torch.cuda.synchronize()
+    assert rel_l2(Rd.cpu(), R2.double().cpu()) < 5e-5
+
+
 def test_gemm_tc_strided_views():
     """conv2d output [B*L, spk*256] re-read as [B*L*spk, 256] (abi.cu masknet_impl) and lda > K."""
     M, K = 777, 256

@@ -23,18 +23,29 @@ VARIANTS = {
     "r64": BASE + ["-DCSE_EPI_ROW_BYTES=64"],
     "r64_nostore": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOSTORE"],
     "r64_noepi": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOEPI"],
+    "ffn_nofinal": BASE + ["-DFFN_DBG_NOFINAL"],
+    "ffn_noe1": BASE + ["-DFFN_DBG_NOE1"],
+    "ffn_loadsonly": BASE + ["-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL", "-DFFN_DBG_NOMMA"],
+    "ffn_nomma": BASE + ["-DFFN_DBG_NOMMA"],
+    "ffn_noe1_nofinal": BASE + ["-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "r128_loadsonly": BASE + ["-DCSE_EPI_ROW_BYTES=128", "-DCSE_DBG_NOEPI", "-DCSE_DBG_NOMMA"],
+    "r128_nomma": BASE + ["-DCSE_EPI_ROW_BYTES=128", "-DCSE_DBG_NOMMA"],
     "r64_nomma": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOMMA"],
 }
 
 
 def build(names):
     os.makedirs(OUT, exist_ok=True)
-    others = [o for o in glob.glob(os.path.join(CSRC, "*.o")) if not o.endswith("gemm_tc.o")]
+    varied = ["gemm_tc", "ffn_tc"]
+    others = [o for o in glob.glob(os.path.join(CSRC, "*.o")) if os.path.basename(o)[:-2] not in varied]
     for name in names or VARIANTS:
-        obj = os.path.join(OUT, f"gemm_tc_{name}.o")
-        subprocess.check_call([NVCC] + FLAGS + VARIANTS[name] + ["-c", os.path.join(CSRC, "gemm_tc.cu"), "-o", obj])
+        objs = []
+        for src in varied:
+            obj = os.path.join(OUT, f"{src}_{name}.o")
+            subprocess.check_call([NVCC] + FLAGS + VARIANTS[name] + ["-c", os.path.join(CSRC, src + ".cu"), "-o", obj])
+            objs.append(obj)
         lib = os.path.join(OUT, f"libcse_{name}.so")
-        subprocess.check_call([NVCC, "-shared", "-o", lib, obj] + others + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + others + ["-gencode", "arch=compute_100a,code=sm_100a"])
         print("built", lib)
 
 
@@ -49,7 +60,7 @@ def run(names):
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.cse_last_error.restype = C.c_char_p
         line = [f"{name:12s} pair={os.environ.get('CSE_GEMM_PAIR', '0')} ares={os.environ.get('CSE_GEMM_ARES', '0')}"]
-        for tag, N, K, relu, resid in shapes:
+        for tag, N, K, relu, resid in (shapes if not name.startswith("ffn_") else []):
             A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
             W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
             b = torch.randn(N, device="cuda")
@@ -74,6 +85,29 @@ def run(names):
                 torch.cuda.synchronize()
                 res.append(e0.elapsed_time(e1) / 20 * 1e3)
             line.append(f"{tag} {res[0]:6.1f}/{res[1]:6.1f}")
+        if hasattr(lib, "cse_ffn_fused"):
+            lib.cse_ffn_fused.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+            A = (torch.randn(M, 256, device="cuda") * 0.5).bfloat16()
+            W1 = (torch.randn(1024, 256, device="cuda") * 0.05).bfloat16()
+            W2 = (torch.randn(256, 1024, device="cuda") * 0.03).bfloat16()
+            b1, b2 = torch.randn(1024, device="cuda"), torch.randn(256, device="cuda")
+            R = torch.zeros(M, 256, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+
+            def ffn():
+                if lib.cse_ffn_fused(A.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                     R.data_ptr(), M, st):
+                    raise RuntimeError(lib.cse_last_error().decode())
+            for _ in range(3):
+                ffn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ffn()
+            e1.record()
+            torch.cuda.synchronize()
+            line.append(f"ffn_fused {e0.elapsed_time(e1) / 20 * 1e3:6.1f}")
         print("  ".join(line) + "   (us with bias / without)", flush=True)
 
 
