@@ -25,8 +25,10 @@
 // clusters of two on adjacent row tiles: every weight box is fetched from L2 once per pair (each CTA
 // loads half of it and multicasts).
 //
-// Roles (320 threads): warp 0 TMA producer | warp 1 single-thread tcgen05.mma issuer | warps 2-9
-// epilogue (TMEM lane quarter = warp & 3, column half = (warp-2) >> 2).  All mbarrier waits are bounded.
+// Roles (448 threads): warp 0 TMA producer | warp 1 single-thread tcgen05.mma issuer | warps 2-9
+// hidden-chunk epilogue E1 (TMEM lane quarter = warp & 3, column half = (warp-2) >> 2) | warps 10-13
+// output epilogue Y -> R (one per lane quarter, two staging chunks each), so E1 of the next tile never
+// waits behind the residual update of the previous one.  All mbarrier waits are bounded.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -40,18 +42,22 @@ int sm_count();
 
 namespace {
 
-constexpr int kFfnThreads = 320;
+constexpr int kFfnThreads = 448;
 constexpr int kD = 256;        // d_model
 constexpr int kH = 1024;       // d_ffn
 constexpr int kHC = 128;       // hidden units per chunk
 constexpr int kChunks = kH / kHC;
 constexpr int kKb = 128 * 128;          // 16 KB: 128 rows x 64 bf16, SWIZZLE_128B
 constexpr int kStageBytes = 2 * kKb;    // 32 KB
-constexpr int kStages = 4;
+#ifndef FFN_STAGES
+#define FFN_STAGES 4
+#endif
+constexpr int kStages = FFN_STAGES;
 constexpr int kABytes = 4 * kKb;        // resident A tile: 4 k-blocks
-constexpr int kStgBytes = 32 * 128;     // per epilogue warp: 32 rows x 32 fp32
+constexpr int kStgBytes = 32 * 128;     // output staging chunk: 32 rows x 32 fp32 (two per output warp)
+constexpr int kBiasBytes = kD * 4;      // b2 (b1 is read through L1)
 constexpr int kOps = 2 * kChunks;
-constexpr size_t kFfnSmem = 1024 + kABytes + kStages * kStageBytes + 8 * kStgBytes + 256;
+constexpr size_t kFfnSmem = 1024 + kABytes + kStages * kStageBytes + 8 * kStgBytes + kBiasBytes + 256;
 
 // op i of the per-tile schedule G1_0 G1_1 G2_0 G1_2 G2_1 ... G1_7 G2_6 G2_7
 __device__ __forceinline__ void decode_op(int i, bool& is_g1, int& j) {
@@ -71,7 +77,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t sA = smem_base;
   const uint32_t sW = sA + kABytes;
   const uint32_t sStg = sW + kStages * kStageBytes;
-  const uint32_t sBar = sStg + 8 * kStgBytes;
+  const uint32_t sBias = sStg + 8 * kStgBytes;
+  const uint32_t sBar = sBias + kBiasBytes;
+  float* s_b2 = reinterpret_cast<float*>(smem_al + (sBias - smem_base));
   const uint32_t bar_wfull = sBar;              // [4]
   const uint32_t bar_wempty = sBar + 32;        // [4]
   const uint32_t bar_afull = sBar + 64;         // [2] k-blocks {0,1} / {2,3} of the resident A tile
@@ -100,9 +108,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(bar_pfull + 8 * i, 8);   // one arrive per epilogue warp
     }
     mbar_init(bar_yfull, 1);
-    mbar_init(bar_yempty, 8);
+    mbar_init(bar_yempty, 4);   // one arrive per output-epilogue warp
     mbar_fence_init();
   }
+  for (int i = threadIdx.x; i < kD; i += kFfnThreads) s_b2[i] = b2[i];
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   fence_before();
   __syncthreads();
@@ -174,7 +183,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (j == 0) mbar_wait_spin(bar_afull + 8 * t, (uint32_t)it & 1u, 5);
               mbar_wait_spin(bar_wfull + 8 * stage, wphase, 6);
               fence_after();
-#ifndef FFN_DBG_NOMMA
+#if !defined(FFN_DBG_NOMMA) && !defined(FFN_DBG_NOG1)
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk) {
                 const uint64_t adesc = make_desc(sA + (2 * t + (kk >> 2)) * kKb, 1024, kLayoutSw128);
@@ -198,7 +207,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               // of Hacc[b] (each epilogue column-half packs into its own columns)
               const uint32_t a_tmem = tmem_h + b * kHC + t * 64;
               const uint64_t bdesc = make_desc(sW + stage * kStageBytes, 1024, kLayoutSw128);
-#ifndef FFN_DBG_NOMMA
+#if !defined(FFN_DBG_NOMMA) && !defined(FFN_DBG_NOG2)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_ts(tmem_y, a_tmem + 8 * k, bdesc + 2 * k, idesc_g2, (j | t | k) != 0 ? 1u : 0u);
@@ -212,25 +221,13 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         __syncwarp();
       }
     }
-  } else {
-    // ================= epilogue warps 2..9 =================
+  } else if (warp < 10) {
+    // ================= hidden-chunk epilogue E1, warps 2..9 =================
     const int q = warp & 3;            // TMEM lane quarter (fixed by hardware: warp id % 4)
     const int h = (warp - 2) >> 2;     // column half
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t stg = sStg + (warp - 2) * kStgBytes;
-    uint4* stg_ptr = reinterpret_cast<uint4*>(smem_al + (stg - smem_base));
-    float bv[64];
-    auto load_b1 = [&](int j) {
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(b1 + j * kHC + h * 64 + i));
-        bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
-      }
-    };
-    load_b1(0);
     int it = 0;
     for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
-      const int row_base = (2 * mp + rank) * 128 + q * 32;
       for (int j = 0; j < kChunks; ++j) {
         const int b = j & 1;
         const uint32_t use = (uint32_t)(it * (kChunks / 2) + (j >> 1));
@@ -239,16 +236,17 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #ifndef FFN_DBG_NOE1
         float v[64];
         tmem_ld64(tmem_h + lane_off + b * kHC + h * 64, v);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + bv[i], 0.f);
-        load_b1((j + 1) & (kChunks - 1));  // next chunk's bias: latency hides behind the pack / waits
-        // pack to bf16 pairs (low half = even hidden unit) and write them over this warp's own first 32
-        // fp32 columns: the A operand of G2_j, read by the tensor core straight from TMEM
+        // bias + ReLU, pack to bf16 pairs (low half = even hidden unit) and write them over this warp's
+        // own first 32 fp32 columns: the A operand of G2_j, read by the tensor core straight from TMEM
         uint32_t pk[32];
+        const float4* bsrc = reinterpret_cast<const float4*>(b1 + j * kHC + h * 64);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&t);
+        for (int i = 0; i < 16; ++i) {
+          const float4 t = __ldg(bsrc + i);  // lane-uniform, L1-resident
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v[4 * i] + t.x, 0.f), fmaxf(v[4 * i + 1] + t.y, 0.f));
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v[4 * i + 2] + t.z, 0.f), fmaxf(v[4 * i + 3] + t.w, 0.f));
+          pk[2 * i] = *reinterpret_cast<const uint32_t*>(&lo);
+          pk[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hi);
         }
         tmem_st32(tmem_h + lane_off + b * kHC + h * 64, pk);
 #endif
@@ -256,25 +254,36 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pfull + 8 * b);
       }
-      // ---- Y + b2 -> R (fp32 residual stream, in place, TMA reduce-add; rows past M are clipped) ----
+    }
+  } else {
+    // ================= output epilogue Y + b2 -> R, warps 10..13 =================
+    // fp32 residual stream updated in place by TMA reduce-add; rows past M are clipped by the tensor map
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t stg0 = sStg + (warp - 10) * 2 * kStgBytes;  // two staging chunks per warp
+    int it = 0;
+    for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
+      const int row_base = (2 * mp + rank) * 128 + q * 32;
       mbar_wait(bar_yfull, (uint32_t)it & 1u, 13);
       fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = h * 128 + c * 32;
+      for (int c = 0; c < 8; ++c) {
+        const int col = c * 32;
         float y[32];
         tmem_ld32(tmem_y + lane_off + col, y);
-        if (c == 3) {  // Y fully read by this warp: the next tile's G2_0 may overwrite it
+        if (c == 7) {  // Y fully read by this warp: the next tile's G2_0 may overwrite it
           fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_yempty);
         }
 #ifndef FFN_DBG_NOFINAL
-        if (lane == 0) bulk_wait_read<0>();  // the previous reduce-add has drained the staging tile
+        const uint32_t stg = stg0 + (c & 1) * kStgBytes;
+        uint4* stg_ptr = reinterpret_cast<uint4*>(smem_al + (stg - smem_base));
+        if (lane == 0) bulk_wait_read<1>();  // the reduce-add issued two chunks ago has drained this staging tile
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(b2 + col + 4 * i));
+          const float4 t = *reinterpret_cast<const float4*>(s_b2 + col + 4 * i);
           uint4 u;
           u.x = __float_as_uint(y[4 * i] + t.x);
           u.y = __float_as_uint(y[4 * i + 1] + t.y);

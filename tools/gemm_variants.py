@@ -23,6 +23,9 @@ VARIANTS = {
     "r64": BASE + ["-DCSE_EPI_ROW_BYTES=64"],
     "r64_nostore": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOSTORE"],
     "r64_noepi": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOEPI"],
+    "ffn_g1only": BASE + ["-DFFN_DBG_NOG2", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_g2only": BASE + ["-DFFN_DBG_NOG1", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_stages3": BASE + ["-DFFN_STAGES=3"],
     "ffn_nofinal": BASE + ["-DFFN_DBG_NOFINAL"],
     "ffn_noe1": BASE + ["-DFFN_DBG_NOE1"],
     "ffn_loadsonly": BASE + ["-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL", "-DFFN_DBG_NOMMA"],
