@@ -25,6 +25,18 @@ VARIANTS = {
     "r64_noepi": BASE + ["-DCSE_EPI_ROW_BYTES=64", "-DCSE_DBG_NOEPI"],
     "ffn_g1only": BASE + ["-DFFN_DBG_NOG2", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
     "ffn_g2only": BASE + ["-DFFN_DBG_NOG1", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_e1spin": BASE + ["-DFFN_E1_SPIN"],
+    "ffn_e1spin_noe1_nofinal": BASE + ["-DFFN_E1_SPIN", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_g1n64": BASE + ["-DFFN_DBG_G1N=64", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_g2n128": BASE + ["-DFFN_DBG_G2N=128", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_g1n64_g2n128": BASE + ["-DFFN_DBG_G1N=64", "-DFFN_DBG_G2N=128", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_solo": BASE + ["-DFFN_SOLO"],
+    "ffn_solo_noe1_nofinal": BASE + ["-DFFN_SOLO", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_solo_loadsonly": BASE + ["-DFFN_SOLO", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL", "-DFFN_DBG_NOMMA"],
+    "ffn_g1ts": BASE + ["-DFFN_DBG_G1TS", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_g1ts_g1only": BASE + ["-DFFN_DBG_G1TS", "-DFFN_DBG_NOG2", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
+    "ffn_trace": BASE + ["-DFFN_TRACE"],
+    "ffn_trace_noe1_nofinal": BASE + ["-DFFN_TRACE", "-DFFN_DBG_NOE1", "-DFFN_DBG_NOFINAL"],
     "ffn_stages3": BASE + ["-DFFN_STAGES=3"],
     "ffn_nofinal": BASE + ["-DFFN_DBG_NOFINAL"],
     "ffn_noe1": BASE + ["-DFFN_DBG_NOE1"],
@@ -111,6 +123,14 @@ def run(names):
             e1.record()
             torch.cuda.synchronize()
             line.append(f"ffn_fused {e0.elapsed_time(e1) / 20 * 1e3:6.1f}")
+            if hasattr(lib, "cse_debug_ffn_trace"):
+                buf = (C.c_ulonglong * (3 * 64))()
+                lib.cse_debug_ffn_trace(buf)
+                t0 = buf[0]
+                print("op:  wait_start  got_dep  (G2: weights)   [cycles since first op, block 0, first 4 tiles]")
+                for k in range(16, 48):
+                    print(f"  {k:2d} {'G1' if (k % 16 == 0 or (k % 16) % 2 == 1) and k % 16 != 15 else 'G2'}"
+                          f" {buf[k] - t0:8d} {buf[64 + k] - t0:8d} {max(0, buf[128 + k] - t0):8d}")
         print("  ".join(line) + "   (us with bias / without)", flush=True)
 
 
