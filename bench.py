@@ -151,6 +151,12 @@ def attention_flops_per_forward(ps):
     return float(16 * (tok_i * 4 * ps.n_intra * N + tok_e * 4 * ps.n_inter * N))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class (tcgen05 GEMMs), from the
+# ncu --set full capture in profiles/r01_ncu_full_layer.txt: mean over the three launches of an intra layer
+# (QKV 224 MB, out-proj 292 MB, fused FFN 292 MB).  A committed measurement, not something bench.py can re-measure.
+GEMM_CLASS_DRAM_BYTES_PER_LAUNCH = 2.696e8
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -268,10 +274,10 @@ def run_ours(args):
         achieved = flops_per_launch / (g_ms / g_n * 1e-3) / 1e12
         a_ms = ms_cls[1] / args.steps
         roofline = {
-            "kernel": "cse::gemm_tc_kernel (tcgen05 + TMA bf16 GEMM, all Linear/1x1-conv layers)",
+            "kernel": "cse::gemm_tc_kernel + cse::ffn_tc_kernel (tcgen05 + TMA bf16 GEMMs: all Linear / 1x1-conv layers, fused FFN)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS)",
-            "traffic": None,
+            "traffic": GEMM_CLASS_DRAM_BYTES_PER_LAUNCH,
             "algorithmic_flops_per_launch": flops_per_launch,
             "avg_launch_ms": g_ms / g_n,
             "kernel_share_of_step": g_ms / ms_step,
