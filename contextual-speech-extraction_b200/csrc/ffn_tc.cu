@@ -14,11 +14,14 @@
 // whatever N <= 256 is, so only N = 256 instructions run at the full rate.  Both GEMMs are therefore
 // issued as 128x256x16 UMMAs and the hidden dimension is walked in 4 chunks of 256 units:
 //   G1_c : Hacc (TMEM, 256 cols) = A(128x256) · W1_c(256x256)^T             16 UMMAs (SS)
-//   E1_c : Hacc -> +b1 -> ReLU -> bf16 pairs -> back into the SAME TMEM columns, in four 64-unit pieces
+//   E1_c : Hacc -> +b1 -> ReLU -> bf16 pairs -> back into the SAME TMEM columns, in four 64-unit pieces;
+//          all eight E1 warps work on the same piece (32 columns each), because tcgen05.ld moves only
+//          ~64 B/clk per SM: reading the 128 KB accumulator takes as long as the 16 UMMAs that made it,
+//          and the first piece must be out after 1/4 of that, not 1/2
 //   G2_c : Y (TMEM, 256 cols) += H_c(128x256, A operand from TMEM) · W2[:, chunk c]^T   16 UMMAs (TS)
 // TMEM is full (Y 256 + Hacc 256 columns), so Hacc is single-buffered; to keep the tensor pipe busy the
-// G2 k-blocks are issued piece by piece as E1 finishes them (order 0,2,1,3: the two column-half warps
-// work in parallel), and G1_{c+1} follows G2_c in pipe order, which is all the protection Hacc needs.
+// G2 k-blocks are issued piece by piece as E1 finishes them, and G1_{c+1} follows G2_c in pipe order,
+// which is all the protection Hacc needs.
 // After G2_3 the output warps add b2 and fold Y into the fp32 residual stream with TMA reduce-add (the
 // stream is never loaded into the SM).
 // Shared memory: A 64 KB (4 k-blocks, resident for the tile) + a 4-stage x 32 KB weight ring (one
@@ -73,7 +76,7 @@ constexpr int kBiasBytes = kD * 4;      // b2 (b1 is read through L1)
 constexpr size_t kFfnSmem = 1024 + kABytes + kStages * kStageBytes + 8 * kStgBytes + kBiasBytes + 256;
 
 // G2 consumes the four 64-unit pieces of a hidden chunk in the order E1 finishes them
-__device__ __forceinline__ int g2_piece(int s) { return ((s & 1) << 1) | (s >> 1); }  // 0,2,1,3
+__device__ __forceinline__ int g2_piece(int s) { return s; }
 
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
@@ -112,7 +115,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
-      mbar_init(bar_pfull + 8 * i, 4);   // the four lane-quarter warps of the piece's column half
+      mbar_init(bar_pfull + 8 * i, 8);   // all eight E1 warps contribute to every piece
     }
     mbar_init(bar_hfull, 1);
     mbar_init(bar_yfull, 1);
@@ -225,24 +228,27 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(bar_hfull, use & 1u, 11);
         fence_after();
 #pragma unroll 1
-        for (int pp = 0; pp < 2; ++pp) {
-          const int p = 2 * h + pp;  // piece: hidden units [64p, 64p+64) of the chunk
+        for (int p = 0; p < 4; ++p) {  // piece: hidden units [64p, 64p+64) of the chunk; this warp: 32 of them
 #ifndef FFN_DBG_NOE1
-          float v[64];
-          tmem_ld64(tmem_h + lane_off + p * 64, v);
-          // bias + ReLU, pack to bf16 pairs (low half = even hidden unit) and write them over the first 32
-          // of the 64 fp32 columns just read: the A operand of G2, read by the tensor core from TMEM
-          uint32_t pk[32];
-          const float4* bsrc = reinterpret_cast<const float4*>(b1 + c * kHC + p * 64);
+          // (issuing the load of piece p+1 before converting piece p was measured slower: it shares the
+          // tcgen05.ld bandwidth with the piece G2 is waiting for)
+          float v[32];
+          tmem_ld32(tmem_h + lane_off + p * 64 + h * 32, v);
+          // bias + ReLU, pack to bf16 pairs (low half = even hidden unit)
+          uint32_t pk[16];
+          const float4* bsrc = reinterpret_cast<const float4*>(b1 + c * kHC + p * 64 + h * 32);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const float4 t = __ldg(bsrc + i);  // lane-uniform, L1-resident
             const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v[4 * i] + t.x, 0.f), fmaxf(v[4 * i + 1] + t.y, 0.f));
             const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v[4 * i + 2] + t.z, 0.f), fmaxf(v[4 * i + 3] + t.w, 0.f));
             pk[2 * i] = *reinterpret_cast<const uint32_t*>(&lo);
             pk[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hi);
           }
-          tmem_st32(tmem_h + lane_off + p * 64, pk);
+          // The packed piece occupies columns [64p, 64p+32): the h = 1 warp writes where the h = 0 warp of
+          // the same lane quarter has just READ, so the two warps meet before either stores.
+          named_bar_sync(1 + q, 64);
+          tmem_st16(tmem_h + lane_off + p * 64 + h * 16, pk);
 #endif
           fence_before();
           __syncwarp();
@@ -261,11 +267,13 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int row_base = (2 * mp + rank) * 128 + q * 32;
       mbar_wait(bar_yfull, (uint32_t)it & 1u, 13);
       fence_after();
+      if (warp == 10 && lane == 0) { FFN_TRACE_PUT(2, it * 16); }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int col = c * 32;
         float y[32];
         tmem_ld32(tmem_y + lane_off + col, y);
+        if (warp == 10 && lane == 0) { FFN_TRACE_PUT(2, it * 16 + 1 + c); }
         if (c == 7) {  // Y fully read by this warp: the next tile's G2_0 may overwrite it
           fence_before();
           __syncwarp();

@@ -127,10 +127,14 @@ def run(names):
                 buf = (C.c_ulonglong * (3 * 64))()
                 lib.cse_debug_ffn_trace(buf)
                 t0 = buf[0]
-                print("op:  wait_start  got_dep  (G2: weights)   [cycles since first op, block 0, first 4 tiles]")
-                for k in range(16, 48):
-                    print(f"  {k:2d} {'G1' if (k % 16 == 0 or (k % 16) % 2 == 1) and k % 16 != 15 else 'G2'}"
-                          f" {buf[k] - t0:8d} {buf[64 + k] - t0:8d} {max(0, buf[128 + k] - t0):8d}")
+                t0 = buf[0]
+                print("MMA thread, block 0: per ring stage [wait_start, deps_ok, weights_ok] in cycles; 8 stages per chunk (4 G1 + 4 G2), 4 chunks per tile")
+                for k in range(0, 64):
+                    print(f"  tile {k // 32} chunk {(k // 8) % 4} {'G1' if k % 8 < 4 else 'G2'}{k % 4}"
+                          f" {buf[k] - t0:8d} {buf[64 + k] - t0:8d}")
+                print("output warp 10, block 0: yfull seen, then after each of the 8 tmem loads")
+                for it in range(3):
+                    print("  tile", it, [int(buf[128 + it * 16 + j] - t0) for j in range(9)])
         print("  ".join(line) + "   (us with bias / without)", flush=True)
 
 
