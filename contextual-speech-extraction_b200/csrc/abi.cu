@@ -184,6 +184,17 @@ static bool ffn_fused_enabled() {
   return on;
 }
 
+// CSE_LN_FUSED=1 runs norm1 -> in_proj as one kernel (gemm_ln_tc.cu).  Off by default: measured 123-132 us
+// against 36 + 67 us for the two kernels (its LayerNorm warps cannot keep enough loads in flight inside the
+// 96 registers a 576-thread CTA leaves them), profiles/r01_experiments.md.
+static bool ln_qkv_fused_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_LN_FUSED");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 // SBTransformerBlock_CSE body after the PE add: 8 pre-norm layers on the fp32 residual stream R
 // (TransformerEncoderLayer.forward, CSE_transformer.py:385-416).  The final LayerNorm belongs to
 // the stack tail (stack_finish / pred_head).
@@ -197,9 +208,16 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
   const int act = pl.precision;
   for (int l = 0; l < CSE_LAYERS; ++l) {
     const cse_layer_params& lp = sp.layer[l];
-    if (launch_layernorm(R, lp.ln1_g, lp.ln1_b, M, 1e-6f, act, H, st)) return 1;
-    if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
-               3 * kN, kN, 0, 0, st)) return 1;
+    if (pl.precision == CSE_BF16 && ln_qkv_fused_enabled()) {
+      // norm1 -> in_proj in one kernel: the residual row is read once and normalised in the GEMM's A producer
+      CSE_REQUIRE(lp.in_proj_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
+      if (launch_gemm_ln_tc(R, lp.ln1_g, lp.ln1_b, 1e-6f, (const bf16*)lp.in_proj_w_bf16, lp.in_proj_b,
+                            (bf16*)QKV, 3 * kN, M, 3 * kN, 0, st)) return 1;
+    } else {
+      if (launch_layernorm(R, lp.ln1_g, lp.ln1_b, M, 1e-6f, act, H, st)) return 1;
+      if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
+                 3 * kN, kN, 0, 0, st)) return 1;
+    }
     if (launch_attention(QKV, nseq, n, act, AO, st)) return 1;
     if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
                0, 1, st)) return 1;

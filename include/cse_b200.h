@@ -201,8 +201,8 @@ CSE_API int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* 
                           const float* b2, float* R, int M, void* stream);
 
 /* Pre-norm sub-block head `norm(src)` -> Linear fused (CSE_transformer.py:385-390 norm1 -> in_proj,
- * :407-411 norm2 -> ffn.0 + ReLU), CSE_BF16 only: C[M,N] bf16 = act(LN(R[M,256]) W[N,256]^T + bias).
- * The fp32 residual row is read once; LayerNorm runs in the GEMM's A-operand producer warps. */
+ * :407-411 norm2 -> ffn.0 + ReLU), CSE_BF16 only: C[M,N] bf16 = act(LN(R[M,256]) W[N,256]^T + bias),
+ * N % 256 == 0.  The fp32 residual row is read once; LayerNorm runs in the GEMM's A-operand producer warps. */
 CSE_API int cse_ln_linear(const float* R, const float* gamma, const float* beta, float eps,
                           const void* W_bf16, const float* bias, void* C, int ldc, int M, int N,
                           int relu, void* stream);

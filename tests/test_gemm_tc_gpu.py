@@ -57,8 +57,8 @@ def test_gemm_tc_epilogues(M, N, K):
     assert rel_l2(r.cpu(), exact + bias.double() + res.double()) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,relu", [(1, 128, 0), (128, 768, 0), (517, 1024, 1), (20000, 768, 0),
-                                      (2 * 148 * 128 + 77, 1024, 1), (3 * 148 * 128 + 5, 128, 0)])
+@pytest.mark.parametrize("M,N,relu", [(1, 256, 0), (128, 768, 0), (129, 768, 0), (517, 1024, 1), (20000, 768, 0),
+                                      (2 * 148 * 128 + 77, 1024, 1), (3 * 148 * 128 + 5, 256, 0)])
 def test_ln_fused_gemm(M, N, relu):
     """cse_ln_linear: LayerNorm in the A-operand producer == LayerNorm kernel -> bf16 -> GEMM."""
     R = _rand(M, 256, seed=7) * 2.0 + 0.3
