@@ -295,24 +295,32 @@ attention_bf16_kernel(const bf16* __restrict__ qkv, int n, int n_pad, bf16* __re
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t mat = (size_t)n_pad * 32;
 
-  // stage Q, K, V rows: 16-byte chunks, coalesced along each row's 64 B; pad rows zero
-  const int chunks = HPC * 3 * n_pad * 4;
-  for (int i = threadIdx.x; i < chunks; i += kThreads) {
-    const int ch = i & 3;
-    int t = i >> 2;
-    const int hh = t % HPC;  // head varies fastest after the chunk: HPC*64 contiguous bytes per (row, matrix)
-    t /= HPC;
-    const int j = t % n_pad, which = t / n_pad;
-    bf16* dst = S + ((size_t)hh * 3 + which) * mat + j * 32 + ((ch ^ ((j >> 1) & 3)) << 3);
-    if (j < n) {
-      // cp.async (LDGSTS): every chunk of the CTA is in flight at once instead of one
-      // load->store round trip per loop iteration
-      const bf16* src = base + (size_t)j * (3 * kN) + which * kN + (h0 + hh) * kDh + ch * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
-                   "l"(src)
-                   : "memory");
-    } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+  // stage Q, K, V rows: 16-byte chunks, coalesced along each row's 64 B; pad rows zero.  Chunk index =
+  // (row, head, 16-byte chunk) with HPC*4 (a power of two) chunks per row, so the decomposition is shifts
+  // and masks only (runtime divisions by n_pad used to be ~40 % of this kernel's instructions at n = 35).
+  constexpr int kCpr = HPC * 4;               // chunks per (row, matrix)
+  constexpr int kRowStep = kThreads / kCpr;   // rows advanced per loop trip: a multiple of 8, so the swizzle
+  {                                           // term (j >> 1) & 3 and everything but the row are loop-invariant
+    const int ch = threadIdx.x & 3;
+    const int hh = (threadIdx.x >> 2) & (HPC - 1);
+    const int j0 = threadIdx.x / kCpr;
+    const bf16* src0 = base + (size_t)j0 * (3 * kN) + (h0 + hh) * kDh + ch * 8;
+    bf16* dst0 = S + (size_t)hh * 3 * mat + j0 * 32 + ((ch ^ ((j0 >> 1) & 3)) << 3);
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      const bf16* src = src0 + which * kN;
+      bf16* dst = dst0 + which * mat;
+      for (int j = j0; j < n_pad; j += kRowStep, src += (size_t)kRowStep * 3 * kN, dst += kRowStep * 32) {
+        if (j < n) {
+          // cp.async (LDGSTS): every chunk of the CTA is in flight at once instead of one
+          // load->store round trip per loop iteration
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                       "l"(src)
+                       : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
     }
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
