@@ -121,7 +121,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
         const int b = k & 1;
         const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        const AtItem it = at_decode(item, n, nseq, g);
+        const AtItem it = at_decode(items - 1 - item, n, nseq, g);  // descending sweep, see launch_attention
         const int nk = it.kv_rows > 128 ? 2 : 1;
         if (lane == 0) {
           // Q/K of this buffer were last read by the S-MMA of item k-2
@@ -147,7 +147,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
         const int b = k & 1;
         const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        const AtItem it = at_decode(item, n, nseq, g);
+        const AtItem it = at_decode(items - 1 - item, n, nseq, g);  // descending sweep, see launch_attention
         const int ncols = (it.kv_rows + 15) & ~15;
         mbar_wait(bar(QK_FULL, b), ph, 22);
         if (k >= 2) mbar_wait(bar(FREE, b), ph ^ 1u, 23);  // O of item k-2 drained from TMEM
@@ -175,7 +175,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       if ((k & 1) != grp) continue;
       const int b = grp;
       const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-      const AtItem it = at_decode(item, n, nseq, g);
+      const AtItem it = at_decode(items - 1 - item, n, nseq, g);  // descending sweep, see launch_attention
       const int ncols = (it.kv_rows + 15) & ~15;
       const int npair = (ncols + 63) >> 6;  // 64-key blocks
       int lo = 0, hi = it.kv_rows;

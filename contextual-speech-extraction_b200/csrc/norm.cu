@@ -3,6 +3,8 @@
 // Reference: sb LayerNorm = nn.LayerNorm(256, eps 1e-6) (CSE_transformer.py:197,358-359,386,408);
 // Dual_Computation_Block_CSE tails (ContSep.py:487-502 intra, :516-531 inter);
 // pred_head (ContSep.py:516-517).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cse {
@@ -13,12 +15,15 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x,
                                                         const float* __restrict__ g,
                                                         const float* __restrict__ b, size_t M,
-                                                        float eps, T* __restrict__ out) {
+                                                        float eps, T* __restrict__ out, int reverse) {
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * 8;
   const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);
-  for (size_t r = warp; r < M; r += nwarps) {
+  for (size_t rr = warp; rr < M; rr += nwarps) {
+    // reverse: sweep from the last row down, i.e. start with the rows the producer of x (a GEMM that walks
+    // the rows upwards) touched last and that are still in L2
+    const size_t r = reverse ? M - 1 - rr : rr;
     f8 v = ld8(x + r * kN + lane * 8);
     ln_row(v, gg, bb, eps);
     st8(out + r * kN + lane * 8, v);
@@ -28,11 +33,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 int launch_layernorm(const float* x, const float* g, const float* b, int M, float eps, int act,
                      void* out, cudaStream_t st) {
   const int grid = (int)min((size_t)148 * 8, ((size_t)M + 7) / 8);
+  const int reverse = 1;  // descending sweep: see launch_attention (attention.cu)
   KernelScope prof(kClsLayerNorm, st);
   if (act == CSE_BF16)
-    layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (bf16*)out);
+    layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (bf16*)out, reverse);
   else
-    layernorm_kernel<float><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (float*)out);
+    layernorm_kernel<float><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (float*)out, reverse);
   return check_launch("layernorm_kernel");
 }
 
@@ -58,7 +64,8 @@ __global__ void __launch_bounds__(256) finish_stats_kernel(const float* __restri
   const f8 gg = ld8(ln_g + lane * 8), bb = ld8(ln_b + lane * 8);
   const int rows = S * kK;
   float sum = 0.f, sq = 0.f;
-  for (int o = blockIdx.x * 8 + wid; o < rows; o += gridDim.x * 8) {
+  for (int oo = blockIdx.x * 8 + wid; oo < rows; oo += gridDim.x * 8) {
+    const int o = rows - 1 - oo;  // descending sweep (the last FFN walked the rows upwards; pass 2 walks up again)
     const int s = o / kK, k = o % kK;
     f8 v = ld8(R + stack_row(b, s, k, S, c, inter) * kN + lane * 8);
     ln_row(v, gg, bb, 1e-6f);
