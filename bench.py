@@ -283,7 +283,7 @@ def run_ours(args):
             "kernel_share_of_step": g_ms / ms_step,
             "classes": share,
             "attention": {"achieved": attention_flops_per_forward(ps) / (a_ms * 1e-3) / 1e12 if a_ms else None,
-                          "unit": "TFLOP/s (QK^T + PV only; kernel is exp-bound)"},
+                          "unit": "TFLOP/s (QK^T + PV only; the kernels are bound by softmax / tcgen05.ld, not by the MMAs)"},
             "whole_step": {"achieved": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12,
                            "unit": "TFLOP/s", "frac": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]},
         }

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) finish_stats_kernel(const float* __restri
                                                            float* __restrict__ gn_part) {
   __shared__ float s_red[2][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.y;
+  const int b = gridDim.y - 1 - blockIdx.y;  // CTAs are scheduled in blockIdx order: last sample first
   const f8 gg = ld8(ln_g + lane * 8), bb = ld8(ln_b + lane * 8);
   const int rows = S * kK;
   float sum = 0.f, sq = 0.f;
