@@ -8,17 +8,18 @@
 //   * n <= 128 ("packed"): floor(128/n) consecutive sequences share a tile; S is block-diagonal and
 //     every row only exponentiates its own sequence's n keys (the inter stack at 2-16 s of audio).
 //   * 128 < n <= 256 ("split"): two query tiles per sequence against all n keys (the intra stack).
-// Pipeline per item (two items in flight per SM, one per 128-thread warp-group; the group's leader
-// thread issues its own PV MMA, a dedicated warp issues the S MMAs, two producer lanes stream Q/K and V):
+// Pipeline per item (two items in flight per SM, one per 128-thread softmax group; warp 1 issues the S
+// MMAs, warp 10 the PV MMAs, two producer lanes of warp 0 stream Q/K and V):
 //   TMA (SWIZZLE_64B boxes of the packed qkv buffer: Q 128x32, K/V up to 256x32)
 //   -> tcgen05.mma  S[128 x Ncols] = Q K^T   (both operands K-major, fp32 accumulators in TMEM)
-//   -> 128 softmax threads, ONE ROW EACH: tcgen05.ld the row in 32-column chunks, exact two-pass
-//      softmax (the whole row is on chip, so no online rescaling): FMNMX pass, then
-//      FFMA + MUFU.EX2 + FADD per score, P packed to bf16 into a SWIZZLE_128B K-major smem tile
-//   -> tcgen05.mma  O[128 x 32] = P V        (A = P from smem, B = V as an MN-major operand, so V
-//      is consumed exactly as TMA wrote it; O overwrites the first 32 columns of S in TMEM)
-//   -> the same threads scale O by 1/rowsum and store bf16.
-// The kernel is MUFU-bound by construction (32768 exp per item vs 4+16 UMMA instructions).
+//   -> 128 softmax threads, ONE ROW EACH, ONE pass over the row in 64-key chunks (tcgen05.ld moves only
+//      ~64 B/clk per SM, so S is read exactly once): online softmax — chunk c is exponentiated against
+//      the running maximum m_c, P_c is packed to bf16 into a SWIZZLE_128B K-major smem k-block
+//   -> tcgen05.mma  O_c[128 x 32] = P_c V_c per chunk, as soon as the four warps of the group have
+//      delivered P_c (A = P from smem, B = V as an MN-major operand, exactly as TMA wrote it); O_c
+//      lands in the first 32 TMEM columns of the chunk's own, already consumed, score columns
+//   -> the same threads read the O_c, re-weight them by 2^(m_c - m_final) (<= 1), divide by the
+//      re-weighted row sum and store bf16.
 #include <mutex>
 #include <unordered_map>
 
@@ -29,12 +30,12 @@ namespace cse {
 
 using namespace tc;
 
-constexpr int kAtThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax group 0, 6-9 group 1
+constexpr int kAtThreads = 352;  // warp 0 TMA, warp 1 S-MMA, warps 2-5 softmax group 0, 6-9 group 1, warp 10 PV-MMA
 constexpr int kAtQ = 128 * 64;        // 8 KB   Q tile  [128 rows x 32 bf16]
 constexpr int kAtKV = 256 * 64;       // 16 KB  K or V  [256 rows x 32 bf16]
 constexpr int kAtP = 4 * 128 * 128;   // 64 KB  P       4 k-blocks of [128 rows x 64 bf16]
 constexpr int kAtBuf = kAtQ + 2 * kAtKV + kAtP;
-constexpr size_t kAtSmem = 1024 + 2 * (size_t)kAtBuf + 256;
+constexpr size_t kAtSmem = 1024 + 2 * (size_t)kAtBuf + 384;
 
 struct AtItem {
   int q_row0, q_rows, kv_row0, kv_rows, head;
@@ -88,7 +89,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   // per buffer b: qk_full, v_full, s_full, o_full, free  (8 bytes each)
   auto bar = [&](int which, int b) -> uint32_t { return sBar + (uint32_t)(which * 2 + b) * 8; };
   enum { QK_FULL = 0, V_FULL = 1, S_FULL = 2, O_FULL = 3, FREE = 4 };
-  const uint32_t tmem_slot = sBar + 10 * 8;
+  auto bar_p = [&](int b, int cp) -> uint32_t { return sBar + (uint32_t)(10 + b * 4 + cp) * 8; };  // P_c written
+  const uint32_t tmem_slot = sBar + 18 * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
   auto sQ = [&](int b) { return smem_base + (uint32_t)b * kAtBuf; };
   auto sK = [&](int b) { return smem_base + (uint32_t)b * kAtBuf + kAtQ; };
@@ -104,6 +106,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       mbar_init(bar(S_FULL, b), 1);
       mbar_init(bar(O_FULL, b), 1);
       mbar_init(bar(FREE, b), 4);
+      for (int cp = 0; cp < 4; ++cp) mbar_init(bar_p(b, cp), 4);  // one arrive per softmax warp of the group
     }
     mbar_fence_init();
   }
@@ -162,13 +165,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       }
     }
     __syncwarp();
+  } else if (warp == 10) {
+    // ================= O_c = P_c V_c issuer (items in order; the softmax warps never block on MMA issue) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+      int k = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+        const int b = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        const AtItem it = at_decode(items - 1 - item, n, nseq, g);  // descending sweep, see launch_attention
+        const int ncols = (it.kv_rows + 15) & ~15;
+        const int npair = (ncols + 63) >> 6;
+        const uint32_t d_o = tmem_base + (uint32_t)b * 256;
+        mbar_wait(bar(V_FULL, b), ph, 21);
+        for (int cp = 0; cp < 4; ++cp) {
+          mbar_wait(bar_p(b, cp), ph, 24);
+          fence_after();
+          const int t1 = (cp < npair) ? min(4 * cp + 4, ncols / 16) : 0;
+          for (int t = 4 * cp; t < t1; ++t) {
+            const uint64_t ad = make_desc(sP(b) + (uint32_t)cp * 16384, 1024, kLayoutSw128) + (uint64_t)(2 * (t & 3));
+            const uint64_t bd = make_desc(sV(b) + (uint32_t)t * 1024, 512, kLayoutSw64);
+            umma_bf16(d_o + (uint32_t)cp * 64, ad, bd, idesc_pv, (t & 3) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar(O_FULL, b));
+      }
+    }
+    __syncwarp();
   } else {
-    // ================= softmax + PV + epilogue groups (128 threads each) =================
-    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+    // ================= softmax + epilogue groups (128 threads each) =================
     const int grp = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
-    const bool leader = (warp == 2 + 4 * grp) && lane == 0;
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
     int k = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
@@ -192,85 +220,84 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
       mbar_wait(bar(S_FULL, b), ph, 30);
       fence_after();
-      // ---- pass 1: row max over [lo, hi) ----
-      float mx = -INFINITY;
-      for (int cp = wlo >> 6; cp <= (whi - 1) >> 6; ++cp) {
-        float v[64];
-        tmem_ld64(taddr + cp * 64, v);
-        const int c0 = cp * 64;
-        if (!(uniform && c0 + 64 <= hi)) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
-        }
-        mx = fmaxf(mx, at_max64(v));
-      }
-      const float msc = mx * sl2;
-      // ---- pass 2: P = 2^(s*sl2 - m), row sum, bf16 P into the swizzled A-operand tile ----
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      // ---- single pass over S: online softmax per 64-key chunk ----
+      float m_run = -INFINITY;
+      float mc[4], lc[4];
       unsigned char* prow = smem_al + (sP(b) - smem_base) + r * 128;
-      for (int cp = 0; cp < npair; ++cp) {
-        const int c0 = cp * 64;
-        uint4* dst = reinterpret_cast<uint4*>(prow + cp * 16384);  // k-block cp: [128 rows x 64 keys]
-        if (c0 + 64 <= wlo || c0 >= whi) {  // warp-uniform: no row of this warp attends these keys
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i ^ (r & 7)] = make_uint4(0u, 0u, 0u, 0u);
-          continue;
-        }
-        float v[64];
-        tmem_ld64(taddr + c0, v);
-        if (uniform && c0 + 64 <= hi) {
+      for (int cp = 0; cp < 4; ++cp) {
+        mc[cp] = -INFINITY;
+        lc[cp] = 0.f;
+        if (cp < npair) {
+          const int c0 = cp * 64;
+          uint4* dst = reinterpret_cast<uint4*>(prow + cp * 16384);  // k-block cp: [128 rows x 64 keys]
+          if (c0 + 64 <= wlo || c0 >= whi) {  // warp-uniform: no row of this warp attends these keys
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = at_ex2(fmaf(v[i], sl2, -msc));
-        } else {
+            for (int i = 0; i < 8; ++i) dst[i ^ (r & 7)] = make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            float v[64];
+            tmem_ld64(taddr + c0, v);
+            if (!(uniform && c0 + 64 <= hi)) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float p = at_ex2(fmaf(v[i], sl2, -msc));
-            v[i] = (c0 + i >= lo && c0 + i < hi) ? p : 0.f;
+              for (int i = 0; i < 64; ++i)
+                if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
+            }
+            const float m_new = fmaxf(m_run, at_max64(v) * sl2);
+            const float msc = (m_new == -INFINITY) ? 0.f : m_new;  // row has no key yet (packed mode)
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = at_ex2(fmaf(v[i], sl2, -msc));  // masked: 2^-inf = 0
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              s0 += v[i];
+              s1 += v[i + 1];
+              s2 += v[i + 2];
+              s3 += v[i + 3];
+            }
+            mc[cp] = m_new;
+            lc[cp] = (s0 + s1) + (s2 + s3);
+            m_run = m_new;
+            // 16-byte chunk i XOR (row & 7): SWIZZLE_128B K-major
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+              h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+              h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              dst[i ^ (r & 7)] = u;
+            }
           }
+          fence_before();        // this warp's reads of the chunk's score columns precede O_c overwriting them
+          fence_proxy_async();   // P_c (generic-proxy stores) visible to the tensor core's async proxy
         }
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          sum0 += v[i];
-          sum1 += v[i + 1];
-          sum2 += v[i + 2];
-          sum3 += v[i + 3];
-        }
-        // 16-byte chunk i XOR (row & 7): SWIZZLE_128B K-major
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 u;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-          h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-          h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-          h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-          h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-          dst[i ^ (r & 7)] = u;
-        }
+        // (chunks past the item's keys are signalled too: the barrier phases must advance once per item)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p(b, cp));
       }
-      const float sum = (sum0 + sum1) + (sum2 + sum3);
-      fence_before();        // TMEM reads of S done before the PV MMA overwrites S[:, 0:32] with O
-      fence_proxy_async();   // P (generic-proxy stores) visible to the tensor core's async proxy
-      named_bar_sync(1 + grp, 128);
-      // ---- O = P V, issued by the group's own leader thread ----
-      if (leader) {
-        mbar_wait(bar(V_FULL, b), ph, 21);
-        fence_after();
-        const uint32_t d_o = tmem_base + (uint32_t)b * 256;  // O overwrites S[:, 0:32]
-        for (int t = 0; t < ncols / 16; ++t) {
-          const uint64_t ad = make_desc(sP(b) + (uint32_t)(t >> 2) * 16384, 1024, kLayoutSw128) + (uint64_t)(2 * (t & 3));
-          const uint64_t bd = make_desc(sV(b) + (uint32_t)t * 1024, 512, kLayoutSw64);
-          umma_bf16(d_o, ad, bd, idesc_pv, t > 0 ? 1u : 0u);
-        }
-        umma_commit(bar(O_FULL, b));
+      // ---- epilogue: O = sum_c 2^(m_c - m) O_c, row sum likewise, O / rowsum -> bf16 ----
+      float fc[4], sum = 0.f;
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        fc[cp] = (mc[cp] == -INFINITY) ? 0.f : at_ex2(mc[cp] - m_run);
+        sum += fc[cp] * lc[cp];
       }
-      __syncwarp();
-      // ---- epilogue: O / rowsum -> bf16 ----
       mbar_wait(bar(O_FULL, b), ph, 31);
       fence_after();
       {
         float o[32];
-        tmem_ld32(taddr, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int cp = 0; cp < 4; ++cp) {
+          if (cp < npair) {
+            float oc[32];
+            tmem_ld32(taddr + cp * 64, oc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = fmaf(fc[cp], oc[i], o[i]);
+          }
+        }
         const float inv = 1.0f / sum;
         if (r < it.q_rows) {
           uint4* dsto = reinterpret_cast<uint4*>(out + (size_t)(it.q_row0 + r) * kN + it.head * kDh);
