@@ -16,7 +16,8 @@
 //   G1_c : Hacc (TMEM, 256 cols) = A(128x256) · W1_c(256x256)^T             16 UMMAs (SS)
 //   E1_c : Hacc -> +b1 -> ReLU -> bf16 pairs -> back into the SAME TMEM columns, in four 64-unit pieces;
 //          all eight E1 warps work on the same piece (32 columns each), because tcgen05.ld moves only
-//          ~64 B/clk per SM: reading the 128 KB accumulator takes as long as the 16 UMMAs that made it,
+//          ~40 B/clk per SM (tools/micro/tmem_ld_rate.cu): reading the 128 KB accumulator takes 1.7x as
+//          long as the 16 UMMAs that made it,
 //          and the first piece must be out after 1/4 of that, not 1/2
 //   G2_c : Y (TMEM, 256 cols) += H_c(128x256, A operand from TMEM) · W2[:, chunk c]^T   16 UMMAs (TS)
 // TMEM is full (Y 256 + Hacc 256 columns), so Hacc is single-buffered; to keep the tensor pipe busy the
