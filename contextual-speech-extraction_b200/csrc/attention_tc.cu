@@ -12,8 +12,7 @@
 // MMAs, warp 10 the PV MMAs, two producer lanes of warp 0 stream Q/K and V):
 //   TMA (SWIZZLE_64B boxes of the packed qkv buffer: Q 128x32, K/V up to 256x32)
 //   -> tcgen05.mma  S[128 x Ncols] = Q K^T   (both operands K-major, fp32 accumulators in TMEM)
-//   -> 128 softmax threads, ONE ROW EACH, ONE pass over the row in 64-key chunks (tcgen05.ld moves only
-//      ~40 B/clk per SM, so S is read exactly once): online softmax — chunk c is exponentiated against
+//   -> 128 softmax threads, ONE ROW EACH, ONE pass over the row in 64-key chunks: online softmax — chunk c is exponentiated against
 //      the running maximum m_c, P_c is packed to bf16 into a SWIZZLE_128B K-major smem k-block
 //   -> tcgen05.mma  O_c[128 x 32] = P_c V_c per chunk, as soon as the four warps of the group have
 //      delivered P_c (A = P from smem, B = V as an MN-major operand, exactly as TMA wrote it); O_c

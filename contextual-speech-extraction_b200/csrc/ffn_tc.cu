@@ -10,15 +10,14 @@
 // accumulator into bf16 pairs in place (tcgen05.ld -> bias/ReLU -> tcgen05.st) and the second GEMM
 // reads it from TMEM as its A operand.
 //
-// Measured on B200 (profiles/): a 128-row UMMA occupies the tensor pipe for ~128 cycles per K=16 step
-// whatever N <= 256 is, so only N = 256 instructions run at the full rate.  Both GEMMs are therefore
-// issued as 128x256x16 UMMAs and the hidden dimension is walked in 4 chunks of 256 units:
+// Measured on B200 (tools/micro/umma_rate.cu): back-to-back 128-row UMMAs into one accumulator cost at least
+// ~96 cycles each however small N is (107 at N = 128), so only N = 256 instructions run near the full rate.
+// Both GEMMs are therefore issued as 128x256x16 UMMAs and the hidden dimension is walked in 4 chunks of 256:
 //   G1_c : Hacc (TMEM, 256 cols) = A(128x256) · W1_c(256x256)^T             16 UMMAs (SS)
 //   E1_c : Hacc -> +b1 -> ReLU -> bf16 pairs -> back into the SAME TMEM columns, in four 64-unit pieces;
-//          all eight E1 warps work on the same piece (32 columns each), because tcgen05.ld moves only
-//          ~40 B/clk per SM (tools/micro/tmem_ld_rate.cu): reading the 128 KB accumulator takes 1.7x as
-//          long as the 16 UMMAs that made it,
-//          and the first piece must be out after 1/4 of that, not 1/2
+//          all eight E1 warps work on the same piece (32 columns each): a piece costs a warp ~500 cycles
+//          (mostly the convert/pack arithmetic, the TMEM load itself is <100), and what the second GEMM
+//          waits for is the FIRST piece
 //   G2_c : Y (TMEM, 256 cols) += H_c(128x256, A operand from TMEM) · W2[:, chunk c]^T   16 UMMAs (TS)
 // TMEM is full (Y 256 + Hacc 256 columns), so Hacc is single-buffered; to keep the tensor pipe busy the
 // G2 k-blocks are issued piece by piece as E1 finishes them, and G1_{c+1} follows G2_c in pipe order,
@@ -48,7 +47,7 @@ int sm_count();
 
 #ifdef FFN_TRACE
 // development aid (tools/gemm_variants.py): per-stage timestamps of block 0, never compiled into the product
-__device__ unsigned long long g_ffn_trace[3][64];
+__device__ unsigned long long g_ffn_trace[4][64];
 #define FFN_TRACE_PUT(role, idx) \
   if (blockIdx.x == 0 && (idx) < 64) g_ffn_trace[role][idx] = clock64()
 extern "C" __attribute__((visibility("default"))) int cse_debug_ffn_trace(unsigned long long* out) {
@@ -59,6 +58,12 @@ extern "C" __attribute__((visibility("default"))) int cse_debug_ffn_trace(unsign
 #endif
 
 namespace {
+
+#ifdef FFN_SOLO
+#define FFN_COMMIT_WEMPTY(bar) umma_commit(bar)
+#else
+#define FFN_COMMIT_WEMPTY(bar) umma_commit_mcast(bar, (uint16_t)3)
+#endif
 
 constexpr int kFfnThreads = 448;
 constexpr int kD = 256;        // d_model
@@ -111,7 +116,11 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
+#ifdef FFN_SOLO
+      mbar_init(bar_wempty + 8 * i, 1);
+#else
       mbar_init(bar_wempty + 8 * i, 2);  // released by the MMA issuers of both CTAs of the pair
+#endif
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
@@ -152,12 +161,20 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             mbar_wait_spin(bar_wempty + 8 * stage, wphase ^ 1u, 2);
             mbar_expect_tx(bar_wfull + 8 * stage, kStageBytes);
+#ifdef FFN_SOLO
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t dst = sW + stage * kStageBytes + hh * kKb;
+              if (s < 4) tma_load_2d(dst, &tmW1, bar_wfull + 8 * stage, s * 64, c * kHC + hh * 128);
+              else tma_load_2d(dst, &tmW2, bar_wfull + 8 * stage, c * kHC + g2_piece(s - 4) * 64, hh * 128);
+            }
+#else
             const uint32_t dst = sW + stage * kStageBytes + rank * kKb;  // this CTA fetches 128 of the 256 rows
             if (s < 4)   // W1 rows [256c, +256) x k-block s
               tma_load_2d_mcast(dst, &tmW1, bar_wfull + 8 * stage, s * 64, c * kHC + rank * 128, (uint16_t)3);
             else         // W2 rows [0, 256) x hidden units [256c + 64p, +64)
               tma_load_2d_mcast(dst, &tmW2, bar_wfull + 8 * stage, c * kHC + g2_piece(s - 4) * 64, rank * 128,
                                 (uint16_t)3);
+#endif
             if (++stage == kStages) { stage = 0; wphase ^= 1u; }
           }
         }
@@ -186,7 +203,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_h, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
 #endif
-            umma_commit_mcast(bar_wempty + 8 * stage, (uint16_t)3);
+            FFN_COMMIT_WEMPTY(bar_wempty + 8 * stage);
             if (c == kChunks - 1) umma_commit(bar_aempty + 8 * kb);  // A k-block free for the next tile
             if (++stage == kStages) { stage = 0; wphase ^= 1u; }
           }
@@ -209,7 +226,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int k = 0; k < 4; ++k)
               umma_bf16_ts(tmem_y, a_tmem + 8 * k, bdesc + 2 * k, idesc, (c | s | k) != 0 ? 1u : 0u);
 #endif
-            umma_commit_mcast(bar_wempty + 8 * stage, (uint16_t)3);
+            FFN_COMMIT_WEMPTY(bar_wempty + 8 * stage);
             if (++stage == kStages) { stage = 0; wphase ^= 1u; }
           }
           if (c == kChunks - 1) umma_commit(bar_yfull);
@@ -228,19 +245,31 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t use = (uint32_t)(it * kChunks + c);
         mbar_wait(bar_hfull, use & 1u, 11);
         fence_after();
+#ifdef FFN_TRACE
+        const bool tr = (warp == 2 && lane == 0 && it == 1 && c == 1);
+        if (tr) { FFN_TRACE_PUT(3, 39); }
+#define E1_STAMP(j) if (tr) { FFN_TRACE_PUT(3, 40 + p * 5 + (j)); }
+#else
+#define E1_STAMP(j)
+#endif
 #pragma unroll 1
         for (int p = 0; p < 4; ++p) {  // piece: hidden units [64p, 64p+64) of the chunk; this warp: 32 of them
 #ifndef FFN_DBG_NOE1
-          // (issuing the load of piece p+1 before converting piece p was measured slower: it shares the
-          // tcgen05.ld bandwidth with the piece G2 is waiting for)
-          float v[32];
-          tmem_ld32(tmem_h + lane_off + p * 64 + h * 32, v);
-          // bias + ReLU, pack to bf16 pairs (low half = even hidden unit)
-          uint32_t pk[16];
+          // (issuing the load of piece p+1 before converting piece p was measured slower)
+          // the piece's 32 bias values are requested BEFORE the TMEM load (an asm the compiler will not move
+          // loads across), so their L1 round trips overlap it
+          float4 bq[8];
           const float4* bsrc = reinterpret_cast<const float4*>(b1 + c * kHC + p * 64 + h * 32);
 #pragma unroll
+          for (int i = 0; i < 8; ++i) bq[i] = __ldg(bsrc + i);  // lane-uniform, L1-resident
+          float v[32];
+          tmem_ld32(tmem_h + lane_off + p * 64 + h * 32, v);
+          E1_STAMP(0)
+          // bias + ReLU, pack to bf16 pairs (low half = even hidden unit)
+          uint32_t pk[16];
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 t = __ldg(bsrc + i);  // lane-uniform, L1-resident
+            const float4 t = bq[i];
             const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v[4 * i] + t.x, 0.f), fmaxf(v[4 * i + 1] + t.y, 0.f));
             const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v[4 * i + 2] + t.z, 0.f), fmaxf(v[4 * i + 3] + t.w, 0.f));
             pk[2 * i] = *reinterpret_cast<const uint32_t*>(&lo);
@@ -248,12 +277,16 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           // The packed piece occupies columns [64p, 64p+32): the h = 1 warp writes where the h = 0 warp of
           // the same lane quarter has just READ, so the two warps meet before either stores.
+          E1_STAMP(1)
           named_bar_sync(1 + q, 64);
+          E1_STAMP(2)
           tmem_st16(tmem_h + lane_off + p * 64 + h * 16, pk);
+          E1_STAMP(3)
 #endif
           fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_pfull + 8 * p);
+          E1_STAMP(4)
         }
       }
     }

@@ -14,9 +14,8 @@
 // staging), so the LayerNorm warps run ONE ROW TILE AHEAD IN REGISTERS: while the tensor core works on
 // row tile i they load and normalise row tile i+1 (16 rows per warp, 64 packed registers per lane) and
 // dump it into shared memory k-block by k-block the moment the last UMMA reading that k-block retires.
-// All UMMAs are 128x256x16 (a 128-row UMMA takes ~128 cycles per K=16 step for any N <= 256, so narrower
-// tiles run at half rate — the reason the first version of this kernel, with 128-wide weight tiles, lost
-// to the unfused path).  CTAs run in clusters of two on adjacent row tiles and multicast the weight tiles.
+// All UMMAs are 128x256x16 (a 128-row UMMA costs >= ~96 cycles however small N is, so 128-wide tiles run
+// at ~60 % of the rate: one reason the first version of this kernel lost to the unfused path).  CTAs run in clusters of two on adjacent row tiles and multicast the weight tiles.
 // Tiles are dealt to CTA pairs as contiguous runs in (row tile, n-tile) order, so the work is balanced to
 // one tile while consecutive tiles share their row tile.
 //

@@ -124,7 +124,7 @@ def run(names):
             torch.cuda.synchronize()
             line.append(f"ffn_fused {e0.elapsed_time(e1) / 20 * 1e3:6.1f}")
             if hasattr(lib, "cse_debug_ffn_trace"):
-                buf = (C.c_ulonglong * (3 * 64))()
+                buf = (C.c_ulonglong * (4 * 64))()
                 lib.cse_debug_ffn_trace(buf)
                 t0 = buf[0]
                 t0 = buf[0]
@@ -132,8 +132,11 @@ def run(names):
                 for k in range(0, 64):
                     print(f"  tile {k // 32} chunk {(k // 8) % 4} {'G1' if k % 8 < 4 else 'G2'}{k % 4}"
                           f" {buf[k] - t0:8d} {buf[64 + k] - t0:8d}")
+                print("E1 warp 2, tile 1 chunk 1: hfull seen", int(buf[192 + 39] - t0), "; per piece [ld done, math done, bar done, st done, arrived]")
+                for pp in range(4):
+                    print("   piece", pp, [int(buf[192 + 40 + pp * 5 + j] - t0) for j in range(5)])
                 print("output warp 10, block 0: yfull seen, then after each of the 8 tmem loads")
-                for it in range(3):
+                for it in range(2):
                     print("  tile", it, [int(buf[128 + it * 16 + j] - t0) for j in range(9)])
         print("  ".join(line) + "   (us with bias / without)", flush=True)
 

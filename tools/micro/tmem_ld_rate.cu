@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(320, 1) k(int nwarps, int with_mma, int iters,
       if (SHAPE == 4) {  // second 8 KB in flight before the wait
         uint32_t r2[64];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 " R64 ", [%64];\ntcgen05.wait::ld.sync.aligned;\n" : O64(r2) : "r"(taddr + 64 - (i & 1) * 64) : "memory");
-        acc ^= r2[i & 63];
+        acc ^= r2[0] ^ r2[31] ^ r2[63];
       }
-      acc ^= r[i & 63];
+      acc ^= r[0] ^ r[31] ^ r[63];  // static indices: a dynamic index would push the 64 registers to local memory
     }
     if (lane == 0 && warp == 2) cyc[blockIdx.x * 2] = clock64() - t0;
     sink[blockIdx.x * 320 + threadIdx.x] = acc;
