@@ -175,6 +175,14 @@ static int linear(const Plan& pl, const void* A, int lda, const float* W32, cons
                           N, K, relu, st);
 }
 
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 // CSE_FFN_FUSED=0 keeps the two-GEMM feed-forward path (A/B aid; the fused kernel is the default)
 static bool ffn_fused_enabled() {
   static const bool on = []() {

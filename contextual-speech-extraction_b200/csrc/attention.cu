@@ -288,6 +288,8 @@ __global__ void __launch_bounds__(256)
 attention_bf16_kernel(const bf16* __restrict__ qkv, int n, int n_pad, bf16* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kThreads = 256;
+  pdl_launch_dependents();
+  pdl_wait();
   bf16* S = reinterpret_cast<bf16*>(smem_raw);  // [HPC][3][n_pad][32]
   const int h0 = (HPC == 1) ? (int)((gridDim.x - 1 - blockIdx.x) % kHeads) : 0;
   // CTAs are scheduled in blockIdx order: walk the sequences from the last one down (see launch_attention)
@@ -372,7 +374,7 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     }
     if (n <= 64) {  // all 8 heads of a sequence in one CTA, one warp per head
       const size_t smem = (size_t)8 * 3 * n_pad * 32 * sizeof(bf16);
-      attention_bf16_kernel<8><<<nseq, 256, smem, st>>>((const bf16*)qkv, n, n_pad, (bf16*)out);
+      launch_pdl(attention_bf16_kernel<8>, dim3(nseq), dim3(256), smem, st, 1, (const bf16*)qkv, n, n_pad, (bf16*)out);
       return check_launch("attention_bf16_kernel<8>");
     }
     const size_t smem = (size_t)3 * n_pad * 32 * sizeof(bf16);
@@ -380,7 +382,7 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
       set_error("attention: sequence of %d tokens does not fit shared memory", n);
       return 1;
     }
-    attention_bf16_kernel<1><<<(unsigned)nseq * kHeads, 256, smem, st>>>((const bf16*)qkv, n, n_pad, (bf16*)out);
+    launch_pdl(attention_bf16_kernel<1>, dim3((unsigned)nseq * kHeads), dim3(256), smem, st, 1, (const bf16*)qkv, n, n_pad, (bf16*)out);
     return check_launch("attention_bf16_kernel<1>");
   }
   const size_t smem = (size_t)n * kDh * sizeof(float) * 2;

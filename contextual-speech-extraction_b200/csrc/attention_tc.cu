@@ -109,11 +109,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     }
     mbar_fence_init();
   }
+  pdl_launch_dependents();
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // prologue done; from here on the previous kernel's output is read
 
   if (warp == 0) {
     // ================= TMA producers: lane 0 streams Q/K, lane 1 streams V =================
@@ -400,7 +402,7 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     return 1;
   }
   const int grid = (int)(items < sms ? items : sms);
-  attention_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tm, out, n, nseq, g, (int)items);
+  launch_pdl(attention_tc_kernel, dim3(grid), dim3(kAtThreads), kAtSmem, st, 1, tm, out, n, nseq, g, (int)items);
   return check_launch("attention_tc_kernel");
 }
 

@@ -124,6 +124,44 @@ struct KernelScope {  // records a CUDA event pair around the launches made in i
   cudaStream_t st_;
 };
 
+// ---- programmatic dependent launch (PDL) ----
+// The kernels of a transformer layer run back to back on one stream.  Launched with the programmatic-
+// serialization attribute, kernel N+1 may be scheduled onto an SM as soon as kernel N's CTA there has
+// retired: its prologue (barrier init, TMEM allocation, descriptor fetch) then overlaps N's tail, and it
+// blocks in pdl_wait() until ALL of N's memory operations are complete and visible.  Every kernel calls
+// pdl_launch_dependents() first and pdl_wait() before its first global read OR write; both are no-ops in a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+bool pdl_enabled();  // abi.cu: CSE_PDL=0 turns the launch attribute off (A/B aid)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -132,13 +132,15 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     mbar_init(bar_yempty, 4);   // one arrive per output-epilogue warp
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < kD; i += kFfnThreads) s_b2[i] = b2[i];
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < kD; i += kFfnThreads) s_b2[i] = b2[i];  // parameter: not produced by the previous kernel
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // prologue done; from here on the previous kernel's output is read and R is updated
   const uint32_t tmem_y = tmem_base;            // columns [0, 256)
   const uint32_t tmem_h = tmem_base + 256;      // columns [256, 512)
 
@@ -378,19 +380,7 @@ int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (m_pairs < max_pairs ? m_pairs : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kFfnThreads);
-  cfg.dynamicSmemBytes = kFfnSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, ffn_tc_kernel, tmA, tmW1, tmW2, tmR, b1, b2, M);
+  cudaError_t le = launch_pdl(ffn_tc_kernel, dim3(grid), dim3(kFfnThreads), kFfnSmem, st, 2, tmA, tmW1, tmW2, tmR, b1, b2, M);
   if (le != cudaSuccess) {
     set_error("ffn_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
     return 1;

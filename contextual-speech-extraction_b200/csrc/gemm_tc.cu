@@ -314,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
                int relu) {
   using Cfg = TcCfg<BN, PAIR, ARES>;
+  pdl_launch_dependents();
   static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
@@ -374,6 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // prologue done; from here on the previous kernel's output is read / this kernel's output written
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -698,19 +700,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>, tmA, tmB, tmC, bias, bias_scale,
+  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
                                       accumulate, C, ldc, M, N, K, relu);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));

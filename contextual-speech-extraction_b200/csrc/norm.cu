@@ -16,10 +16,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ g,
                                                         const float* __restrict__ b, size_t M,
                                                         float eps, T* __restrict__ out, int reverse) {
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * 8;
-  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);
+  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);  // parameters: not produced by the previous kernel
+  pdl_wait();
   for (size_t rr = warp; rr < M; rr += nwarps) {
     // reverse: sweep from the last row down, i.e. start with the rows the producer of x (a GEMM that walks
     // the rows upwards) touched last and that are still in L2
@@ -36,9 +38,9 @@ int launch_layernorm(const float* x, const float* g, const float* b, int M, floa
   const int reverse = 1;  // descending sweep: see launch_attention (attention.cu)
   KernelScope prof(kClsLayerNorm, st);
   if (act == CSE_BF16)
-    layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (bf16*)out, reverse);
+    launch_pdl(layernorm_kernel<bf16>, dim3(grid), dim3(256), 0, st, 1, x, g, b, (size_t)M, eps, (bf16*)out, reverse);
   else
-    layernorm_kernel<float><<<grid, 256, 0, st>>>(x, g, b, (size_t)M, eps, (float*)out, reverse);
+    launch_pdl(layernorm_kernel<float>, dim3(grid), dim3(256), 0, st, 1, x, g, b, (size_t)M, eps, (float*)out, reverse);
   return check_launch("layernorm_kernel");
 }
 
