@@ -17,6 +17,7 @@
 //    Short sequences (inter stack at 2-8 s of audio, n <= 64) put all 8 heads of a sequence in
 //    one CTA (one warp per head); long ones use one CTA per (sequence, head).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cse {
 
@@ -187,8 +188,8 @@ __device__ __forceinline__ void attn_block(TileState& st, const uint32_t (&qa)[2
       if (key >= n) s[nt][0] = s[nt][2] = -INFINITY;
       if (key + 1 >= n) s[nt][1] = s[nt][3] = -INFINITY;
     }
-    bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
-    bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+    bm0 = tc::max3_f32(bm0, s[nt][0], s[nt][1]);  // FMNMX3
+    bm1 = tc::max3_f32(bm1, s[nt][2], s[nt][3]);
   }
   bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
   bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
@@ -212,10 +213,12 @@ __device__ __forceinline__ void attn_block(TileState& st, const uint32_t (&qa)[2
     float p[2][4];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      p[u][0] = ex2_approx(fmaf(s[kt * 2 + u][0], sl2, -mn0));
-      p[u][1] = ex2_approx(fmaf(s[kt * 2 + u][1], sl2, -mn0));
-      p[u][2] = ex2_approx(fmaf(s[kt * 2 + u][2], sl2, -mn1));
-      p[u][3] = ex2_approx(fmaf(s[kt * 2 + u][3], sl2, -mn1));
+      tc::fma_f32x2(s[kt * 2 + u][0], s[kt * 2 + u][1], sl2, -mn0);  // FFMA2: two scores per instruction
+      tc::fma_f32x2(s[kt * 2 + u][2], s[kt * 2 + u][3], sl2, -mn1);
+      p[u][0] = ex2_approx(s[kt * 2 + u][0]);
+      p[u][1] = ex2_approx(s[kt * 2 + u][1]);
+      p[u][2] = ex2_approx(s[kt * 2 + u][2]);
+      p[u][3] = ex2_approx(s[kt * 2 + u][3]);
       st.l0 += p[u][0] + p[u][1];
       st.l1 += p[u][2] + p[u][3];
     }

@@ -65,16 +65,20 @@ __device__ __forceinline__ float at_ex2(float x) {
   return y;
 }
 
-// max over 64 values with four independent chains (a serial fmaxf chain costs 64 x 4 cycles)
+// max over 64 values: four independent chains of three-input FMNMX3 (a serial fmaxf chain costs 64 x 4 cycles)
 __device__ __forceinline__ float at_max64(const float (&v)[64]) {
   float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-  for (int i = 4; i < 64; i += 4) {
-    m0 = fmaxf(m0, v[i]);
-    m1 = fmaxf(m1, v[i + 1]);
-    m2 = fmaxf(m2, v[i + 2]);
-    m3 = fmaxf(m3, v[i + 3]);
+  for (int i = 4; i < 60; i += 8) {
+    m0 = max3_f32(m0, v[i], v[i + 4]);
+    m1 = max3_f32(m1, v[i + 1], v[i + 5]);
+    m2 = max3_f32(m2, v[i + 2], v[i + 6]);
+    m3 = max3_f32(m3, v[i + 3], v[i + 7]);
   }
+  m0 = fmaxf(m0, v[60]);
+  m1 = fmaxf(m1, v[61]);
+  m2 = fmaxf(m2, v[62]);
+  m3 = fmaxf(m3, v[63]);
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
@@ -245,15 +249,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             }
             const float m_new = fmaxf(m_run, at_max64(v) * sl2);
             const float msc = (m_new == -INFINITY) ? 0.f : m_new;  // row has no key yet (packed mode)
-#pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = at_ex2(fmaf(v[i], sl2, -msc));  // masked: 2^-inf = 0
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-              s0 += v[i];
-              s1 += v[i + 1];
-              s2 += v[i + 2];
-              s3 += v[i + 3];
+            for (int i = 0; i < 64; i += 4) {  // FFMA2 for the scale/shift, MUFU.EX2, FADD2 for the row sum
+              fma_f32x2(v[i], v[i + 1], sl2, -msc);
+              fma_f32x2(v[i + 2], v[i + 3], sl2, -msc);
+              v[i] = at_ex2(v[i]);  // masked: 2^-inf = 0
+              v[i + 1] = at_ex2(v[i + 1]);
+              v[i + 2] = at_ex2(v[i + 2]);
+              v[i + 3] = at_ex2(v[i + 3]);
+              add_f32x2(s0, s1, v[i], v[i + 1]);
+              add_f32x2(s2, s3, v[i + 2], v[i + 3]);
             }
             mc[cp] = m_new;
             lc[cp] = (s0 + s1) + (s2 + s3);

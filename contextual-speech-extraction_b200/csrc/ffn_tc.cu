@@ -270,12 +270,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           // bias + ReLU, pack to bf16 pairs (low half = even hidden unit)
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; ++i) {  // two packed adds + two ReLU-fused conversions per four hidden units
             const float4 t = bq[i];
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v[4 * i] + t.x, 0.f), fmaxf(v[4 * i + 1] + t.y, 0.f));
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v[4 * i + 2] + t.z, 0.f), fmaxf(v[4 * i + 3] + t.w, 0.f));
-            pk[2 * i] = *reinterpret_cast<const uint32_t*>(&lo);
-            pk[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+            add_f32x2(v[4 * i], v[4 * i + 1], t.x, t.y);
+            add_f32x2(v[4 * i + 2], v[4 * i + 3], t.z, t.w);
+            pk[2 * i] = cvt_bf16x2_relu(v[4 * i], v[4 * i + 1]);
+            pk[2 * i + 1] = cvt_bf16x2_relu(v[4 * i + 2], v[4 * i + 3]);
           }
           // The packed piece occupies columns [64p, 64p+32): the h = 1 warp writes where the h = 0 warp of
           // the same lane quarter has just READ, so the two warps meet before either stores.
@@ -324,11 +324,13 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 t = *reinterpret_cast<const float4*>(s_b2 + col + 4 * i);
+          add_f32x2(y[4 * i], y[4 * i + 1], t.x, t.y);
+          add_f32x2(y[4 * i + 2], y[4 * i + 3], t.z, t.w);
           uint4 u;
-          u.x = __float_as_uint(y[4 * i] + t.x);
-          u.y = __float_as_uint(y[4 * i + 1] + t.y);
-          u.z = __float_as_uint(y[4 * i + 2] + t.z);
-          u.w = __float_as_uint(y[4 * i + 3] + t.w);
+          u.x = __float_as_uint(y[4 * i]);
+          u.y = __float_as_uint(y[4 * i + 1]);
+          u.z = __float_as_uint(y[4 * i + 2]);
+          u.w = __float_as_uint(y[4 * i + 3]);
           stg_ptr[lane * 8 + (i ^ (lane & 7))] = u;  // SWIZZLE_128B, conflict-free
         }
         fence_proxy_async();

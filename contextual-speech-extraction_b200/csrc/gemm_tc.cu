@@ -518,13 +518,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tmem_ld16(t_row + col_local, v);
         if (bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] += bv[i];
+          for (int i = 0; i < CW; i += 2) tc::add_f32x2(v[i], v[i + 1], bv[i], bv[i + 1]);  // FADD2
           // prefetch the bias of the chunk this warp handles next (this tile's next chunk, or the first
           // chunk of its next tile): the load latency hides behind the pack/store and the next wait
           const int npt = pt + t_step;
           load_bias(ch + 1 < kNch ? col0 + CW : (npt < t_end ? (npt % n_tiles) * BN : n0) + cgroup * GW);
         }
-        if (relu) {
+        if (relu && OUT_F32) {  // (bf16 outputs fuse the ReLU into the conversion below)
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
         }
@@ -540,12 +540,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             u.y = __float_as_uint(v[4 * i + 1]);
             u.z = __float_as_uint(v[4 * i + 2]);
             u.w = __float_as_uint(v[4 * i + 3]);
+          } else if (relu) {
+            u.x = tc::cvt_bf16x2_relu(v[8 * i], v[8 * i + 1]);
+            u.y = tc::cvt_bf16x2_relu(v[8 * i + 2], v[8 * i + 3]);
+            u.z = tc::cvt_bf16x2_relu(v[8 * i + 4], v[8 * i + 5]);
+            u.w = tc::cvt_bf16x2_relu(v[8 * i + 6], v[8 * i + 7]);
           } else {
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            h[0] = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-            h[1] = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-            h[2] = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-            h[3] = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+            u.x = tc::cvt_bf16x2(v[8 * i], v[8 * i + 1]);
+            u.y = tc::cvt_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = tc::cvt_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = tc::cvt_bf16x2(v[8 * i + 6], v[8 * i + 7]);
           }
           stg[lane * kSlots + (i ^ sw)] = u;
         }

@@ -151,6 +151,41 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
 }
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2) and bf16x2 conversion with fused ReLU ----
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {  // (a0,a1) += (b0,b1)
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+  unpack_f32x2(r, a0, a1);
+}
+__device__ __forceinline__ void fma_f32x2(float& a0, float& a1, float s, float c) {  // (a0,a1) = (a0,a1)*s + c
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(s, s)), "l"(pack_f32x2(c, c)));
+  unpack_f32x2(r, a0, a1);
+}
+__device__ __forceinline__ float max3_f32(float a, float b, float c) {  // FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;\n" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {       // low half = lo
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu(float lo, float hi) {  // max(x, 0) fused into the conversion
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // fp32 x4 reduction into global memory (no return value): R[addr..addr+3] += {a,b,c,d}
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
