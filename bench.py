@@ -153,8 +153,8 @@ def attention_flops_per_forward(ps):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class (tcgen05 GEMMs), from the
 # ncu --set full capture in profiles/r01_ncu_full_layer.txt: mean over the three launches of an intra layer
-# (QKV 224 MB, out-proj 292 MB, fused FFN 292 MB).  A committed measurement, not something bench.py can re-measure.
-GEMM_CLASS_DRAM_BYTES_PER_LAUNCH = 2.696e8
+# (QKV 223 MB, out-proj 291 MB, fused FFN 291 MB).  A committed measurement, not something bench.py can re-measure.
+GEMM_CLASS_DRAM_BYTES_PER_LAUNCH = 2.682e8
 
 
 def run_ours(args):
