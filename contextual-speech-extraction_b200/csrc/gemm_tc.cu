@@ -479,15 +479,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stg0 = sEpi + (warp - 2) * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
     unsigned char* stg0_ptr = smem_aligned + (stg0 - smem_base);
     uint32_t astage = 0, aphase = 0, chunk_ctr = 0;
-    float bv[CW];  // bias_scale * bias of the upcoming chunk (lane-uniform), prefetched one chunk ahead
+    float bv[CW];  // bias of the upcoming chunk (lane-uniform), prefetched one chunk ahead
     auto load_bias = [&](int col) {
 #pragma unroll
       for (int i = 0; i < CW; i += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + i));
-        bv[i] = bias_scale * b4.x;
-        bv[i + 1] = bias_scale * b4.y;
-        bv[i + 2] = bias_scale * b4.z;
-        bv[i + 3] = bias_scale * b4.w;
+        bv[i] = b4.x;  // bias_scale is applied in the packed FMA below
+        bv[i + 1] = b4.y;
+        bv[i + 2] = b4.z;
+        bv[i + 3] = b4.w;
       }
     };
     if (bias != nullptr && t_begin < t_end) load_bias((t_begin % n_tiles) * BN + cgroup * GW);
@@ -518,7 +518,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tmem_ld16(t_row + col_local, v);
         if (bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < CW; i += 2) tc::add_f32x2(v[i], v[i + 1], bv[i], bv[i + 1]);  // FADD2
+          for (int i = 0; i < CW; i += 2) tc::axpy_f32x2(v[i], v[i + 1], bv[i], bv[i + 1], bias_scale);  // FFMA2
           // prefetch the bias of the chunk this warp handles next (this tile's next chunk, or the first
           // chunk of its next tile): the load latency hides behind the pack/store and the next wait
           const int npt = pt + t_step;

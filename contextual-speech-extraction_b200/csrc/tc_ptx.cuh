@@ -170,6 +170,11 @@ __device__ __forceinline__ void fma_f32x2(float& a0, float& a1, float s, float c
   asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(s, s)), "l"(pack_f32x2(c, c)));
   unpack_f32x2(r, a0, a1);
 }
+__device__ __forceinline__ void axpy_f32x2(float& a0, float& a1, float b0, float b1, float s) {  // (a0,a1) += s*(b0,b1)
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(pack_f32x2(b0, b1)), "l"(pack_f32x2(s, s)), "l"(pack_f32x2(a0, a1)));
+  unpack_f32x2(r, a0, a1);
+}
 __device__ __forceinline__ float max3_f32(float a, float b, float c) {  // FMNMX3
   float r;
   asm("max.f32 %0, %1, %2, %3;\n" : "=f"(r) : "f"(a), "f"(b), "f"(c));
