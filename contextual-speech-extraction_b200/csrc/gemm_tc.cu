@@ -6,17 +6,22 @@
 // A is row-major activations, W is the nn.Linear weight [out,in]: BOTH are K-major, which is the
 // native UMMA operand layout, so no transposes exist anywhere.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      : TMA producer — 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B,
-//                 mbarrier complete_tx
+// Structure (persistent, warp-specialised, one CTA per SM, clusters of two CTAs on adjacent row tiles):
+//   warp 0      : TMA producer — 128x64 A tile + HALF of the BNx64 W tile per stage (the other half is
+//                 multicast in by the peer CTA), SWIZZLE_128B, mbarrier complete_tx
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
 //                 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the
 //                 MMAs of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / bf16 pack ->
-//                 128B-swizzled shared-memory chunk -> TMA store.  The fp32 residual update
+//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 64 columns) -> bias (FFMA2, prefetched one chunk
+//                 ahead) / ReLU fused into the bf16 conversion -> 128B-swizzled shared-memory chunk ->
+//                 TMA store.  The fp32 residual update
 //                 R += A W^T + b is a TMA REDUCE-ADD (cp.reduce.async.bulk.tensor .add), so the
 //                 residual stream is never loaded into the SM; the M tail is clipped by TMA.
-// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+// Opt-in variants, measured slower and kept for A/B runs (profiles/r01_experiments.md, tests/test_variants_gpu.py):
+// PAIR = cta_group::2 UMMA over the CTA pair (CSE_GEMM_PAIR=1), ARES = A tile resident across n-tiles
+// (CSE_GEMM_ARES=1).  CSE_DBG_* macros strip parts of the kernel for tools/gemm_variants.py.
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.  The kernel is launched
+// with programmatic dependent launch: its prologue overlaps the previous kernel's tail (pdl_wait()).
 #include <cuda.h>
 
 #include <cstdlib>
