@@ -24,6 +24,13 @@ class LayerParams(C.Structure):
         "in_proj_w_bf16", "out_proj_w_bf16", "ffn1_w_bf16", "ffn2_w_bf16")]
 
 
+class LayerGrads(C.Structure):
+    """cse_layer_grads: gradient buffers of one transformer layer (accumulated into)."""
+    _fields_ = [(n, _v) for n in (
+        "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b",
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
 class StackParams(C.Structure):
     _fields_ = [("layer", LayerParams * LAYERS), ("final_g", _v), ("final_b", _v), ("pe", _v)]
 
@@ -80,6 +87,17 @@ _SIGNATURES = {
     "cse_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v]),
     "cse_pit_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
     "cse_tm_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, _v, _v]),
+    "cse_si_snr_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_pit_si_snr_bwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_tm_si_snr_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_linear_bwd": (C.c_int, [_v, C.c_int, _v, _v, C.c_int, C.c_int, C.c_int, C.c_int, _v, C.c_int, _v, _v,
+                                 _v, _v]),
+    "cse_layernorm_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_float, C.c_int, _v, _v, _v, _v]),
+    "cse_attention_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v]),
+    "cse_layer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "cse_layer_fwd": (C.c_int, [C.POINTER(LayerParams), _v, C.c_int, C.c_int, C.c_int, _v, C.c_size_t, _v]),
+    "cse_layer_bwd": (C.c_int, [C.POINTER(LayerParams), C.POINTER(LayerGrads), _v, _v, C.c_int, C.c_int, _v,
+                                C.c_size_t, _v]),
 }
 
 _lock = threading.Lock()

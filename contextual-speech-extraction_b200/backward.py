@@ -1,0 +1,102 @@
+"""Host side of the training path: hand-written CUDA gradients behind torch.autograd.
+
+The reference trains through autograd (`loss.backward()`, train_ContSep.py:402-419,
+train_ContExt.py:372-389).  Here each differentiable unit of the hot path is an
+`autograd.Function` whose forward AND backward are C-ABI calls (`cse_layer_fwd` / `cse_layer_bwd`,
+`cse_*_si_snr` / `cse_*_si_snr_bwd`): PyTorch only carries the graph, the parameter ownership and
+the `.grad` buffers (so stock DDP gradient all-reduce applies unchanged).  No CPU / eager fallback.
+
+Built so far (fp32 parity mode): one pre-norm transformer layer (TransformerEncoderLayer.forward,
+CSE_transformer.py:385-416) with activation checkpointing at layer granularity, and the three
+SI-SNR losses (in losses.py).  The layer Function is what the 32-layer stacks are made of; the
+GroupNorm / chunking / head / encoder-decoder gradients are the next step.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .runtime import current_stream
+
+LAYER_KEYS = (
+    ("in_proj_w", "self_att.att.in_proj_weight"), ("in_proj_b", "self_att.att.in_proj_bias"),
+    ("out_proj_w", "self_att.att.out_proj.weight"), ("out_proj_b", "self_att.att.out_proj.bias"),
+    ("ffn1_w", "pos_ffn.ffn.0.weight"), ("ffn1_b", "pos_ffn.ffn.0.bias"),
+    ("ffn2_w", "pos_ffn.ffn.3.weight"), ("ffn2_b", "pos_ffn.ffn.3.bias"),
+    ("ln1_g", "norm1.norm.weight"), ("ln1_b", "norm1.norm.bias"),
+    ("ln2_g", "norm2.norm.weight"), ("ln2_b", "norm2.norm.bias"),
+)
+
+
+def _check(t, name):
+    if not t.is_cuda:
+        raise _lib.CseError(f"{name} is on {t.device}: the CUDA path has no CPU fallback")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.CseError(f"{name} must be a contiguous float32 tensor (got {t.dtype})")
+    return t
+
+
+def _layer_struct(params, cls):
+    """params: {reference key relative to the layer prefix -> tensor}."""
+    s = cls()
+    for field, key in LAYER_KEYS:
+        setattr(s, field, C.c_void_p(_check(params[key], key).data_ptr()))
+    return s
+
+
+def _workspace(nseq, n, device):
+    nbytes = _lib.load().cse_layer_workspace_bytes(nseq, n)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def layer_forward(params, R, nseq, n):
+    """TransformerEncoderLayer.forward in fp32 on the residual stream R [nseq*n, 256]; returns a new tensor."""
+    _check(R, "R")
+    if R.shape != (nseq * n, _lib.N):
+        raise _lib.CseError(f"R has shape {tuple(R.shape)}, expected {(nseq * n, _lib.N)}")
+    out = R.clone()
+    ws, nbytes = _workspace(nseq, n, R.device)
+    lp = _layer_struct(params, _lib.LayerParams)
+    _lib.call("cse_layer_fwd", C.byref(lp), _lib.ptr(out), nseq, n, _lib.FP32, _lib.ptr(ws), nbytes,
+              C.c_void_p(current_stream(R.device)))
+    return out
+
+
+def layer_backward(params, R_in, dR_out, nseq, n, grads=None):
+    """Gradient of layer_forward: returns (dR_in, grads) with grads keyed like `params`.
+    `grads` may carry existing buffers to accumulate into (autograd .grad semantics)."""
+    _check(R_in, "R_in")
+    _check(dR_out, "dR_out")
+    if grads is None:
+        grads = {key: torch.zeros_like(params[key]) for _, key in LAYER_KEYS}
+    dR = dR_out.clone()
+    ws, nbytes = _workspace(nseq, n, R_in.device)
+    lp = _layer_struct(params, _lib.LayerParams)
+    lg = _layer_struct(grads, _lib.LayerGrads)
+    _lib.call("cse_layer_bwd", C.byref(lp), C.byref(lg), _lib.ptr(R_in), _lib.ptr(dR), nseq, n, _lib.ptr(ws),
+              nbytes, C.c_void_p(current_stream(R_in.device)))
+    return dR, grads
+
+
+class _LayerFn(torch.autograd.Function):
+    """One transformer layer as an autograd node: saves only its input (checkpointing)."""
+
+    @staticmethod
+    def forward(ctx, R, nseq, n, *weights):
+        params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
+        ctx.save_for_backward(R, *weights)
+        ctx.shape = (nseq, n)
+        return layer_forward(params, R.contiguous(), nseq, n)
+
+    @staticmethod
+    def backward(ctx, dR_out):
+        R, *weights = ctx.saved_tensors
+        nseq, n = ctx.shape
+        params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
+        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n)
+        return (dR, None, None) + tuple(grads[key] for _, key in LAYER_KEYS)
+
+
+def transformer_layer(params, R, nseq, n):
+    """Differentiable fp32 transformer layer: R [nseq*n,256] -> same, gradients by cse_layer_bwd."""
+    return _LayerFn.apply(R, nseq, n, *[params[key] for _, key in LAYER_KEYS])

@@ -221,6 +221,21 @@ int launch_pit(const float* source, const float* est, int B, int T, int C, float
                cudaStream_t st);
 int launch_tm_si_snr(const float* preds, const float* target, int B, int T, float* out,
                      cudaStream_t st);
+int launch_si_snr_bwd(const float* source, const float* estimate, int B, int T, int C, int mode,
+                      const float* gout, const int* perm, float* d_source, float* d_estimate,
+                      cudaStream_t st);
+int launch_tm_si_snr_bwd(const float* preds, const float* target, int B, int T, const float* gout,
+                         float* d_preds, float* d_target, cudaStream_t st);
+// backward.cu (fp32 training path)
+int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st);
+int launch_wgrad(const float* X, int ldx, const float* Y, int ldy, int M, int N1, int N2, float* dW,
+                 cudaStream_t st);
+int launch_colsum(const float* dC, int ld, int M, int N, float* db, cudaStream_t st);
+int launch_relu_bwd(const float* F, float* d, size_t n, cudaStream_t st);
+int launch_layernorm_bwd(const float* x, const float* g, const float* dy, int M, float eps, float* dx,
+                         int accumulate, float* dg, float* db, cudaStream_t st);
+int launch_attention_bwd(const float* qkv, const float* out, const float* d_out, int nseq, int n,
+                         float* d_qkv, cudaStream_t st);
 // pack.cu (in abi.cu)
 int launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
 

@@ -274,6 +274,74 @@ CSE_API int cse_pit_si_snr(const float* source, const float* estimate_source, in
 CSE_API int cse_tm_si_snr(const float* preds, const float* target, int B, int T,
                           float* out, void* stream);
 
+/* ---- backward (training step, BASELINE configs[2]) ----
+ * The reference trains through autograd (`loss.backward()`, train_ContSep.py:402-419,
+ * train_ContExt.py:372-389); these entry points are the hand-written gradients of the same
+ * operators, in true-fp32 arithmetic (parity mode).  Parameter gradients are ACCUMULATED (+=) into
+ * caller-owned buffers, like autograd's .grad; zero them before the first micro-step. */
+
+/* d cal_si_snr / d(source, estimate): g_out [B,C] = dL/d out of cse_si_snr -> d_source, d_estimate
+ * [B,T,C] (either may be NULL).  Overwrites. */
+CSE_API int cse_si_snr_bwd(const float* source, const float* estimate, const float* g_out,
+                           int B, int T, int C, float* d_source, float* d_estimate, void* stream);
+
+/* d get_si_snr_with_pitwrapper: g_loss [B], perm [B,C] as returned by cse_pit_si_snr (the chosen
+ * permutation is a constant of the backward pass, as in PitWrapper) -> d_source, d_estimate_source. */
+CSE_API int cse_pit_si_snr_bwd(const float* source, const float* estimate_source, const float* g_loss,
+                               const int* perm, int B, int T, int C, float* d_source,
+                               float* d_estimate_source, void* stream);
+
+/* d torchmetrics SI-SNR: g_out [B] -> d_preds, d_target [B,T] (either may be NULL). */
+CSE_API int cse_tm_si_snr_bwd(const float* preds, const float* target, const float* g_out, int B, int T,
+                              float* d_preds, float* d_target, void* stream);
+
+/* nn.Linear backward for C = A W^T + bias (fp32): dC [M,N] ->
+ *   dA [M,K] = dC W            (overwritten; NULL to skip; needs scratch_wt [N*K] floats)
+ *   dW [N,K] += dC^T A         (NULL to skip)      dbias [N] += column sums of dC (NULL to skip)
+ * N, K multiples of 128 (N of 256 when dbias is given). */
+CSE_API int cse_linear_bwd(const float* A, int lda, const float* W, const float* dC, int lddc,
+                           int M, int N, int K, float* dA, int ldda, float* dW, float* dbias,
+                           float* scratch_wt, void* stream);
+
+/* nn.LayerNorm(256) backward: x, dy [M,256] -> dx (+= when accumulate != 0), dg/db [256] += . */
+CSE_API int cse_layernorm_bwd(const float* x, const float* g, const float* dy, int M, float eps,
+                              int accumulate, float* dx, float* dg, float* db, void* stream);
+
+/* Attention core backward: qkv [nseq*n,768], out [nseq*n,256] (forward result), d_out -> d_qkv
+ * [nseq*n,768] (overwritten).  n <= 390. */
+CSE_API int cse_attention_bwd(const float* qkv, const float* out, const float* d_out, int nseq, int n,
+                              float* d_qkv, void* stream);
+
+/* Gradient buffers of one transformer layer (same shapes as cse_layer_params' fp32 members). */
+typedef struct {
+  float* in_proj_w;
+  float* in_proj_b;
+  float* out_proj_w;
+  float* out_proj_b;
+  float* ffn1_w;
+  float* ffn1_b;
+  float* ffn2_w;
+  float* ffn2_b;
+  float* ln1_g;
+  float* ln1_b;
+  float* ln2_g;
+  float* ln2_b;
+} cse_layer_grads;
+
+/* TransformerEncoderLayer.forward (CSE_transformer.py:385-416) on the fp32 residual stream, in place:
+ * R [nseq*n,256].  precision as cse_forward.  Workspace: cse_layer_workspace_bytes. */
+CSE_API size_t cse_layer_workspace_bytes(int nseq, int n);
+CSE_API int cse_layer_fwd(const cse_layer_params* p_host, float* R, int nseq, int n, int precision,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the same layer from its INPUT residual stream (activation checkpointing at layer
+ * granularity: the layer is recomputed in fp32, then differentiated):
+ *   R_in [M,256] (layer input, unchanged), dR [M,256]: in = dL/dR_out, out = dL/dR_in;
+ *   grads_host: parameter gradients, accumulated. */
+CSE_API int cse_layer_bwd(const cse_layer_params* p_host, const cse_layer_grads* grads_host,
+                          const float* R_in, float* dR, int nseq, int n,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

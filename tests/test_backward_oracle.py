@@ -1,0 +1,115 @@
+"""CPU: the closed-form gradients the CUDA backward kernels implement (oracle/backward_oracle.py
+`manual_*`) against autograd over the pinned forward oracle — and, where /root/reference exists,
+against autograd over the reference's own TransformerEncoderLayer."""
+import os
+
+import pytest
+import torch
+
+from helpers import rel_l2
+from oracle import backward_oracle as BO
+from oracle import sepformer_oracle as O
+from cse_b200 import synth
+
+
+def _layer_params(seed, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"self_att.att.in_proj_weight": (768, 256), "self_att.att.in_proj_bias": (768,),
+              "self_att.att.out_proj.weight": (256, 256), "self_att.att.out_proj.bias": (256,),
+              "pos_ffn.ffn.0.weight": (1024, 256), "pos_ffn.ffn.0.bias": (1024,),
+              "pos_ffn.ffn.3.weight": (256, 1024), "pos_ffn.ffn.3.bias": (256,),
+              "norm1.norm.weight": (256,), "norm1.norm.bias": (256,),
+              "norm2.norm.weight": (256,), "norm2.norm.bias": (256,)}
+    p = {}
+    for k, s in shapes.items():
+        if k.endswith("norm.weight"):
+            p[k] = (1 + 0.1 * torch.randn(s, generator=g)).to(dtype)
+        elif len(s) == 1:
+            p[k] = (0.1 * torch.randn(s, generator=g)).to(dtype)
+        else:
+            p[k] = (torch.randn(s, generator=g) / s[1] ** 0.5).to(dtype)
+    return p
+
+
+@pytest.mark.parametrize("Bp,n", [(3, 7), (2, 37)])
+def test_manual_layer_backward_matches_autograd(Bp, n):
+    p = _layer_params(11)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(Bp, n, 256, generator=g).double()
+    dy = torch.randn(Bp, n, 256, generator=g).double()
+    _, dx_ref, g_ref = BO.autograd_layer(p, x, dy)
+    dx, grads = BO.manual_layer_bwd(p, x, dy)
+    assert rel_l2(dx, dx_ref) < 1e-12
+    for k in BO.LAYER_KEYS:
+        assert rel_l2(grads[k], g_ref[k]) < 1e-12, k
+
+
+def test_manual_attention_forward_is_the_oracle_attention():
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(2, 19, 768, generator=g).double()
+    o, _ = BO.manual_attention_bwd(qkv, torch.zeros(2, 19, 256).double())
+    sd = {"att.in_proj_weight": torch.eye(768, 256).double(), "att.in_proj_bias": torch.zeros(768).double(),
+          "att.out_proj.weight": torch.eye(256).double(), "att.out_proj.bias": torch.zeros(256).double()}
+    # oracle MHA on an input whose projection IS qkv: feed qkv through identity-free path instead
+    E = 256
+    q, k, v = (t.view(2, 19, 8, 32).transpose(1, 2) for t in qkv.split(E, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 32 ** 0.5, -1) @ v).transpose(1, 2).reshape(2, 19, E)
+    assert rel_l2(o, ref) < 1e-13
+    del sd
+
+
+@pytest.mark.parametrize("kind,C", [("cal_si_snr", 2), ("pit", 2), ("pit", 3), ("tm", 1)])
+def test_manual_loss_gradients_match_autograd(kind, C):
+    B, T = 2, 1500
+    _, a = synth.make_mixture(B, T, max(C, 2), seed=21)
+    _, b = synth.make_mixture(B, T, max(C, 2), seed=22)
+    a, b = a[:, :, :C].double(), b[:, :, :C].double()
+    est = 0.6 * a + 0.4 * b.flip(-1)
+    if kind == "cal_si_snr":
+        src_t, est_t = a.transpose(0, 1), est.transpose(0, 1)            # [T,B,C]
+        _, ds_ref, de_ref = BO.autograd_loss(kind, src_t, est_t)
+        ds = torch.zeros_like(a)
+        de = torch.zeros_like(a)
+        for bi in range(B):
+            for c in range(C):
+                ds[bi, :, c], de[bi, :, c] = BO.manual_sb_pair_grad(a[bi, :, c], est[bi, :, c])
+        assert rel_l2(ds.transpose(0, 1), ds_ref) < 1e-9
+        assert rel_l2(de.transpose(0, 1), de_ref) < 1e-9
+    elif kind == "pit":
+        _, perms = O.pit_si_snr(est, a)
+        _, ds_ref, de_ref = BO.autograd_loss(kind, est, a)                # training order: (estimate, targets)
+        ds, de = BO.manual_pit_grad(est, a, perms)
+        assert rel_l2(ds, ds_ref) < 1e-9
+        assert rel_l2(de, de_ref) < 1e-9
+    else:
+        p, t = est[:, :, 0], a[:, :, 0]
+        # torchmetrics takes eps = finfo(input dtype).eps: differentiate in float32 like the reference does
+        _, dp_ref, dt_ref = BO.autograd_loss(kind, p.float(), t.float())
+        dp, dt = BO.manual_tm_grad(p, t)
+        assert rel_l2(dp, dp_ref) < 1e-5
+        assert rel_l2(dt, dt_ref) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="live reference not present")
+def test_oracle_layer_gradients_match_live_reference():
+    """Pin: autograd over the reference's own TransformerEncoderLayer == autograd over the oracle."""
+    from oracle import run_reference
+    run_reference._paths()
+    from src.models import CSE_transformer as ref_mod
+    layer = ref_mod.TransformerEncoderLayer(d_ffn=1024, nhead=8, d_model=256, dropout=0.0, normalize_before=True)
+    layer = layer.double().eval()
+    p = _layer_params(31)
+    layer.load_state_dict(p, strict=True)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 23, 256, generator=g).double()
+    dy = torch.randn(2, 23, 256, generator=g).double()
+    xi = x.clone().requires_grad_(True)
+    out = layer(xi)
+    out = out[0] if isinstance(out, tuple) else out
+    out.backward(dy)
+    y, dx, grads = BO.autograd_layer(p, x, dy)
+    assert rel_l2(y, out.detach()) < 1e-12
+    assert rel_l2(dx, xi.grad) < 1e-11
+    named = dict(layer.named_parameters())
+    for k in BO.LAYER_KEYS:
+        assert rel_l2(grads[k], named[k].grad) < 1e-11, k
