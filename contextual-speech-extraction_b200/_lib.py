@@ -94,6 +94,13 @@ _SIGNATURES = {
                                  _v, _v]),
     "cse_layernorm_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_float, C.c_int, _v, _v, _v, _v]),
     "cse_attention_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v]),
+    "cse_groupnorm_fwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, C.c_float, _v, _v, _v, _v]),
+    "cse_groupnorm_bwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, _v, _v, _v, _v, _v]),
+    "cse_sequences_to_chunks": (C.c_int, [_v, C.c_int, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_prelu_overlap_add_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_gate_bwd": (C.c_int, [_v, _v, _v, C.c_size_t, _v, _v, _v]),
+    "cse_mask_decode_bwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, C.c_int, C.c_int, _v, _v, _v, _v]),
+    "cse_encoder_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v]),
     "cse_layer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cse_layer_fwd": (C.c_int, [C.POINTER(LayerParams), _v, C.c_int, C.c_int, C.c_int, _v, C.c_size_t, _v]),
     "cse_layer_bwd": (C.c_int, [C.POINTER(LayerParams), C.POINTER(LayerGrads), _v, _v, C.c_int, C.c_int, _v,

@@ -48,7 +48,8 @@ _warned_grad = [False]
 def _warn_no_grad(module):
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()) and not _warned_grad[0]:
         _warned_grad[0] = True
-        warnings.warn("cse_b200: forward kernels only so far — outputs carry no autograd graph")
+        warnings.warn("cse_b200: the bf16 / autocast backward kernels are not built yet — these outputs carry no "
+                      "autograd graph; run the training step in fp32 (precision='fp32', no autocast)")
 
 
 def select_norm(norm, dim, shape, eps=1e-8):
@@ -518,8 +519,15 @@ class _SepformerBase(nn.Module):
         if mix.dim() != 2:
             raise RuntimeError(f"mix must be [B,T], got {tuple(mix.shape)}")
         _check_cuda(mix, "mix")
-        _warn_no_grad(self)
         prec = resolve_precision(self.precision)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (ctx is not None and ctx.requires_grad)):
+            if prec == FP32:
+                # training step (train_ContSep.py:384-419, train_ContExt.py:366-389): the same stages as
+                # autograd nodes whose forward AND backward are C-ABI calls (training.py)
+                from . import training
+                return training.forward_train(self._tensors(), mix, ctx, n_masks, want_pred_head)
+            _warn_no_grad(self)
         dev = mix.device
         stream = current_stream(dev)
         mix = mix.contiguous().float()

@@ -342,6 +342,47 @@ CSE_API int cse_layer_bwd(const cse_layer_params* p_host, const cse_layer_grads*
                           const float* R_in, float* dR, int nseq, int n,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training path, non-transformer stages (fp32; csrc/train_ops.cu) ---- */
+
+/* select_norm('ln') = nn.GroupNorm(1,256,eps) over x [B,rows,256] per sample (ContSep.py:164,226,
+ * 423-424), optionally fused with the block skip connection (ContSep.py:498-502,527-531):
+ * out = (x-mean)*rstd*g + b (+ skip).  stat [B,2] = (mean, rstd) is kept for the backward pass;
+ * part_scratch holds B*64*2 floats. */
+CSE_API int cse_groupnorm_fwd(const float* x, const float* g, const float* b, const float* skip,
+                              int B, int rows, float eps, float* out, float* stat,
+                              float* part_scratch, void* stream);
+/* dx overwritten, dg/db [256] accumulated (NULL to skip).  d skip = dy (identity; left to the caller). */
+CSE_API int cse_groupnorm_bwd(const float* x, const float* stat, const float* g, const float* dy,
+                              int B, int rows, float* dx, float* dg, float* db,
+                              float* part_scratch, void* stream);
+
+/* Inverse relayout of cse_build_sequences (ContSep.py:487-489 / :518-521 `[:, c:]` + permutes, and the
+ * adjoint of the forward relayout): R [nseq*n,256] -> X [B,S,K,256] without the c context rows (X may
+ * be NULL); ctok_sum [B,c,256] = per-sample sum of the context rows over all sequences (the gradient
+ * of the broadcast prompt token; NULL to skip). */
+CSE_API int cse_sequences_to_chunks(const float* R, int B, int S, int c, int inter, float* X,
+                                    float* ctok_sum, void* stream);
+
+/* Backward of cse_prelu_overlap_add (fp32): dU [B,L,256] -> dX [B,S,K,256] (overwritten),
+ * dprelu [1] accumulated (NULL to skip).  With prelu = 1 the forward is exactly the adjoint of
+ * cse_segment, so segmentation needs no backward kernel of its own. */
+CSE_API int cse_prelu_overlap_add_bwd(const float* X, const float* prelu, const float* dU,
+                                      int B, int S, int L, float* dX, float* dprelu, void* stream);
+
+/* Backward of cse_gate: y = tanh(o) * sigmoid(g); d_o, d_g overwritten. */
+CSE_API int cse_gate_bwd(const float* o, const float* g, const float* d_out, size_t n,
+                         float* d_o, float* d_g, void* stream);
+
+/* Backward of cse_mask_decode (fp32, E != NULL): d_est [B,T,n_masks] -> d_mask_pre [B*L*n_masks,256]
+ * and dE [B,L,256] (both overwritten), d_dec_w [256,16] accumulated (NULL to skip). */
+CSE_API int cse_mask_decode_bwd(const float* mask_pre, const float* E, const float* dec_w,
+                                const float* d_est, int B, int L, int T, int n_masks,
+                                float* d_mask_pre, float* dE, float* d_dec_w, void* stream);
+
+/* Backward of cse_encoder_fwd (fp32): d_w [256,16] += sum dE * (E > 0) * frames(mix). */
+CSE_API int cse_encoder_bwd(const float* mix, const float* E, const float* dE, int B, int T,
+                            float* d_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,7 +145,9 @@ def test_attention_backward(nseq, n):
     dqkv = torch.empty(nseq, n, 768, device=DEV)
     _lib.call("cse_attention_bwd", _lib.ptr(qd), _lib.ptr(out), _lib.ptr(dod), nseq, n, _lib.ptr(dqkv), _st())
     for name, sl in (("dq", slice(0, 256)), ("dk", slice(256, 512)), ("dv", slice(512, 768))):
-        assert rel_l2(dqkv.cpu()[..., sl], dqkv_ref[..., sl]) < TOL, name
+        got, ref = dqkv.cpu()[..., sl].double(), dqkv_ref[..., sl]
+        # n == 1: softmax of a single score is constant, dq = dk = 0 exactly (the reference holds rounding noise)
+        assert (got - ref).norm() <= TOL * max(ref.norm().item(), 1e-3), name
     with pytest.raises(_lib.CseError):
         _lib.call("cse_attention_bwd", _lib.ptr(qd), _lib.ptr(out), _lib.ptr(dod), 1, 1000, _lib.ptr(dqkv), _st())
 
