@@ -13,6 +13,9 @@ e2e    : same metric through the host-buffer C-ABI entry (cse_forward_host): pin
 roofline / cpu_baseline: see DESIGN.md §Measurement.
 --impl reference: the oracle port of the reference's CPU path (the Python reference itself cannot
 travel to the GPU box), all host threads, one 4 s mixture per step.
+--workload train (not the driver's default): BASELINE configs[2] — ContExt forward + -SI-SNR loss +
+backward + gradient all-reduce (stock DDP over NCCL) + clip + AdamW, 2 mixtures x 4 s per GPU, fp32
+parity-mode kernels (the bf16 tensor-core backward is not built yet).
 """
 import argparse
 import ctypes as C
@@ -311,15 +314,177 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+TRAIN_BATCH = 2
+
+
+def cpu_train_rate(steps, warmup):
+    """Oracle port, forward + backward of the ContExt loss under autograd, one mixture per step."""
+    import torch
+    import cse_b200  # noqa: F401
+    from cse_b200 import synth
+    from oracle import sepformer_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: (v.requires_grad_(True) if "pos_enc" not in k else v)
+          for k, v in synth.make_state_dict("context", SPK, seed=0).items()}
+    mix, src = synth.make_mixture(1, T, SPK, seed=1234)
+    ctx = synth.make_context(1, CTX_TOKENS, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        est = O.sepformer_forward(sd, mix, ctx, "context", SPK)
+        loss = -O.tm_si_snr(est[:, :, 0], src[:, :, 0]).mean()
+        loss.backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return SECONDS / per_step, per_step, cores
+
+
+def run_train(args):
+    """BASELINE configs[2]: ContExt forward+backward, batch 2 per GPU, data-parallel (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import cse_b200  # noqa: F401
+    from cse_b200 import _lib, losses, shapes, synth
+    from cse_b200.models.ContExt import Sepformer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    model = Sepformer(SPK, add_ctx=True)
+    model.add_ctx_pipeline()
+    model.load_state_dict(synth.make_state_dict("context", SPK, seed=0))
+    model = model.to(dev).train()
+    model.precision = "fp32"
+    net = model
+    if world > 1:   # the reference's own wrapper (train_ContExt.py:269-273): bucketed NCCL all-reduce overlapped with backward
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, amsgrad=True)      # train_ContSep.py:233
+    sisnr = losses.ScaleInvariantSignalNoiseRatio()
+
+    mix_h, src_h = synth.make_mixture(TRAIN_BATCH, T, SPK, seed=4321 + rank)
+    ctx_h = synth.make_context(TRAIN_BATCH, CTX_TOKENS, seed=4321 + rank)
+    tgt_h = src_h[:, :, 0].contiguous().pin_memory()
+    mix_h, ctx_h = mix_h.pin_memory(), ctx_h.pin_memory()
+    mix_d, ctx_d, tgt_d = mix_h.to(dev), ctx_h.to(dev), tgt_h.to(dev)
+
+    def step(mix, ctx, tgt):
+        opt.zero_grad(set_to_none=True)
+        est = net(mix, ctx)
+        loss = -sisnr(est[:, :, 0], tgt)                                    # train_ContExt.py:366-367
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)             # train_ContSep.py:411
+        opt.step()
+        return loss
+
+    def step_device():
+        return step(mix_d, ctx_d, tgt_d)
+
+    def step_host():
+        loss = step(mix_h.to(dev, non_blocking=True), ctx_h.to(dev, non_blocking=True),
+                    tgt_h.to(dev, non_blocking=True))
+        return loss.item()                                                  # D2H of the step's loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        sync_all()
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = t[0].item(), t[1].item() / 1e3
+        return ms, wall
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.lines.clear()
+    n0 = lib.cse_launch_count()
+    step_device()
+    launches = lib.cse_launch_count() - n0
+    ms_total, _ = timed(step_device, args.steps)
+    ms_step = ms_total / args.steps
+    audio_s = TRAIN_BATCH * SECONDS * world
+    value = audio_s / (ms_step / 1e3)
+    _, wall = timed(step_host, args.steps)
+    e2e_value = audio_s / (wall / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    roofline = cpu = None
+    if rank == 0:
+        ps = shapes.path_shape(TRAIN_BATCH, T, CTX_TOKENS, 1)
+        peaks = load_peaks()
+        # forward + recomputed forward (layer checkpointing) + dgrad + wgrad = 4x the forward contractions
+        flops = 4.0 * shapes.algorithmic_flops(ps)
+        achieved = flops / (ms_step * 1e-3) / 1e12
+        roofline = {"kernel": "whole step: cse::gemm_simt_kernel / wgrad_kernel / attention_f32 + attention_bwd (fp32 FFMA parity mode)",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops_sustained"], "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS)",
+                    "traffic": None,
+                    "note": "fp32 SIMT kernels: this fraction is against the bf16 tensor peak the tcgen05 backward will be held to"}
+        if world == 1:
+            v, per_step, cores = cpu_train_rate(2, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"1 mixture ({SECONDS} s) forward+backward per step under autograd, 2 timed steps + 1 warm-up, fp32 oracle port, {cores} threads"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ContExt 2-spk forward + -SI-SNR loss + backward + grad all-reduce + clip + AdamW (BASELINE.json configs[2])",
+                       "batch_per_gpu": TRAIN_BATCH, "seconds": SECONDS, "sample_rate": SR, "ctx_tokens": CTX_TOKENS,
+                       "num_spks": SPK, "weights": "random-init (seeded)",
+                       "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
+                       "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TRAIN_BATCH * (2 * T + CTX_TOKENS * 4096) * 4,
+                    "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+                    help="forward = BASELINE configs[1] (the driver's contract); train = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

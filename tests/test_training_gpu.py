@@ -66,10 +66,7 @@ def test_groupnorm_forward_backward(B, rows, skip):
     out = training.GroupNormFn.apply(xg, gg, bg, skg)
     assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-5
     out.backward(dy.to(DEV))
-    if rows > 1:
-        assert rel_l2(xg.grad.cpu(), xr.grad) < TOL
-    else:                                         # a single row: dx is pure cancellation noise around 0
-        assert xg.grad.abs().max().item() < 1e-3
+    assert rel_l2(xg.grad.cpu(), xr.grad) < TOL
     assert rel_l2(gg.grad.cpu(), gr.grad) < TOL
     assert rel_l2(bg.grad.cpu(), br.grad) < TOL
     if skip:
@@ -89,7 +86,7 @@ def test_segment_and_overlap_add_backward(B, L):
     X = training.SegmentFn.apply(xg, S)                                       # [B,S,K,256]
     assert torch.equal(X.detach().cpu(), seg.detach().permute(0, 3, 2, 1).float())
     X.backward(dseg.permute(0, 3, 2, 1).contiguous().to(DEV))
-    assert rel_l2(xg.grad.cpu(), xr.grad.transpose(1, 2)) < 1e-6
+    assert rel_l2(xg.grad.cpu(), xr.grad) < 1e-6
     # PReLU + overlap-add
     Xc = _rand(B, S, 250, 256, seed=11)
     a = torch.tensor([0.25])
