@@ -23,3 +23,15 @@ LOSS_CASES = {
     "pit_b2_t3000_c3": ("pit", 2, 3000, 3, 33),
     "tm_si_snr_b4_t5000": ("tm_si_snr", 4, 5000, 1, 34),
 }
+
+# Gradient fixtures (make_golden_grads.py): name -> (model case, loss kind).  The REFERENCE model in
+# train() mode, its own loss objects, `loss.backward()`; stored per parameter: gradient norm + the first
+# 64 flattened gradient values.
+#   tm_neg_sisnr : -ScaleInvariantSignalNoiseRatio()(est[:, :, 0], gt)            train_ContExt.py:366-367
+#   pit_plus_sel : get_si_snr_with_pitwrapper(est, gt).mean() + 0.1 * logsumexp(context_pred).mean()
+#                  (PIT SI-SNR of train_ContSep.py:391-393 plus a term that reaches pred_head / context_selector)
+GRAD_CASES = {
+    "grad_context_2spk_b2_t3000": ("context_2spk_b2_t3000", "tm_neg_sisnr"),
+    "grad_contsep_2spk_bce_b1_t2024": ("contsep_2spk_bce_b1_t2024", "pit_plus_sel"),
+}
+GRAD_HEAD = 64

@@ -113,3 +113,47 @@ def test_oracle_layer_gradients_match_live_reference():
     named = dict(layer.named_parameters())
     for k in BO.LAYER_KEYS:
         assert rel_l2(grads[k], named[k].grad) < 1e-11, k
+
+
+def _oracle_training_grads(model_name, kind):
+    from helpers import model_case
+    sd, mix, src, ctx, se, meta = model_case(model_name)
+    sd64 = {k: (v.double().requires_grad_(True) if "pos_enc" not in k else v) for k, v in sd.items()}
+    out = O.sepformer_forward(sd64, mix.double(), ctx.double(), meta["variant"], meta["spk"])
+    if kind == "tm_neg_sisnr":
+        loss = -O.tm_si_snr(out[:, :, 0].float(), src[:, :, 0].float()).mean().double()
+    else:
+        est, pred = out
+        pit, _ = O.pit_si_snr(est, src[:, :, : meta["spk"]].double())
+        loss = pit.mean() + 0.1 * torch.logsumexp(pred, -1).mean()
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in sd64.items() if v.requires_grad}
+
+
+@pytest.mark.parametrize("name", ["grad_context_2spk_b2_t3000", "grad_contsep_2spk_bce_b1_t2024"])
+def test_oracle_gradients_match_reference_golden(name):
+    """Pin of the gradient oracle: autograd over oracle/sepformer_oracle.py against the gradients the
+    REFERENCE's own modules and loss objects produced (tests/golden/make_golden_grads.py)."""
+    import numpy as np
+    from cases import GRAD_CASES, GRAD_HEAD
+    from helpers import GOLDEN
+    model_name, kind = GRAD_CASES[name]
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        gold_loss, names = float(z["loss"]), [str(n) for n in z["names"]]
+        norms, heads = torch.from_numpy(z["norms"]), torch.from_numpy(z["heads"])
+    loss, grads = _oracle_training_grads(model_name, kind)
+    assert abs(loss - gold_loss) < 1e-3, (loss, gold_loss)
+    assert set(names) == set(grads)
+    total = norms.norm().item()
+    worst = 0.0
+    for i, k in enumerate(names):
+        g = grads[k] if grads[k] is not None else torch.zeros(1, dtype=torch.float64)
+        # the fixture is the reference's fp32 arithmetic: compare at fp32-accumulation accuracy, relative
+        # to the parameter's own gradient norm (floored for the parameters whose gradient is ~0)
+        scale = max(norms[i].item(), 1e-6 * total)
+        assert abs(g.norm().item() - norms[i].item()) < 3e-3 * scale, k
+        flat = g.flatten()[:GRAD_HEAD]
+        err = (flat - heads[i, : flat.numel()].double()).norm().item() / scale
+        worst = max(worst, err)
+        assert err < 3e-3, (k, err)
+    print(f"{name}: oracle vs reference gradients, worst head error {worst:.2e} of the parameter's gradient norm")

@@ -136,3 +136,44 @@ def test_sharded_separation_two_ranks_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_training_entry_points_validate_arguments_before_any_launch():
+    """The backward / training C-ABI entry points reject bad shapes and NULL pointers with a
+    message (no CUDA call is reached, so this runs without a GPU)."""
+    import ctypes as C
+    lib = _lib.load()
+    p = C.c_void_p(0x1000)                       # never dereferenced: every call below fails validation first
+    n = 4 * 36
+    per_row = 256 + 768 + 256 + 256 + 1024 + 1024 + 256
+    assert lib.cse_layer_workspace_bytes(4, 36) == n * per_row * 4 + 1024 * 256 * 4
+    assert lib.cse_layer_workspace_bytes(0, 36) == 0
+    cases = [
+        ("cse_linear_bwd", (p, 256, p, p, 300, 10, 300, 256, None, 256, p, None, None, None), "multiples of 128"),
+        ("cse_linear_bwd", (None, 256, p, p, 256, 10, 256, 256, None, 256, p, None, None, None), "NULL"),
+        ("cse_attention_bwd", (p, p, p, 1, 1000, p, None), "does not fit shared memory"),
+        ("cse_gate_bwd", (p, p, p, 12, p, p, None), "multiple of 8"),
+        ("cse_mask_decode_bwd", (p, p, p, p, 1, 10, 100, 5, p, p, None, None), "n_masks=5"),
+        ("cse_encoder_bwd", (p, p, p, 1, 8, p, None), "shorter than the encoder kernel"),
+        ("cse_groupnorm_bwd", (p, p, p, p, 0, 10, p, None, None, p, None), "bad argument"),
+        ("cse_sequences_to_chunks", (p, 1, 4, 1, 0, None, None, None), "bad argument"),
+        ("cse_si_snr_bwd", (p, p, None, 1, 100, 2, p, p, None), "bad argument"),
+        ("cse_layer_bwd", (None, None, p, p, 1, 10, p, 0, None), "bad argument"),
+    ]
+    for name, args, msg in cases:
+        with pytest.raises(_lib.CseError, match=msg):
+            _lib.call(name, *args)
+    lp, lg = _lib.LayerParams(), _lib.LayerGrads()
+    with pytest.raises(_lib.CseError, match="workspace too small"):
+        _lib.call("cse_layer_bwd", C.byref(lp), C.byref(lg), p, p, 4, 36, C.c_void_p(0x10000), 16, None)
+    with pytest.raises(_lib.CseError, match="256-byte aligned"):
+        _lib.call("cse_layer_fwd", C.byref(lp), p, 4, 36, 0, C.c_void_p(0x10010), 1 << 30, None)
+
+
+def test_losses_and_training_refuse_cpu_tensors():
+    from cse_b200 import losses, training
+    a = torch.zeros(2, 100, 2)
+    with pytest.raises(_lib.CseError):
+        losses.get_si_snr_with_pitwrapper(a, a)
+    with pytest.raises(_lib.CseError):
+        training.forward_train({}, torch.zeros(1, 4000), None, 2)
