@@ -123,6 +123,21 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    if getattr(args, "workload", "forward") == "train":
+        value, per_step, cores = cpu_train_rate(steps, warmup)
+        sample = (f"1 mixture x {SECONDS} s forward + -SI-SNR + backward under autograd per step ({steps} timed steps, "
+                  f"{warmup} warm-up), fp32, oracle port of the reference modules")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ContExt 2-spk forward+backward (BASELINE.json configs[2]); bounded sample: 1 of the 2 mixtures per step, no optimizer step",
+                       "batch_per_step": 1, "seconds": SECONDS, "sample_rate": SR, "ctx_tokens": CTX_TOKENS},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }), flush=True)
+        return
     value, per_step, cores = cpu_reference_rate(steps, warmup)
     sample = f"1 mixture x {SECONDS} s per step ({steps} timed steps, {warmup} warm-up), fp32, oracle port of the reference modules"
     print(json.dumps({
