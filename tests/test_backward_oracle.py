@@ -157,3 +157,26 @@ def test_oracle_gradients_match_reference_golden(name):
         worst = max(worst, err)
         assert err < 3e-3, (k, err)
     print(f"{name}: oracle vs reference gradients, worst head error {worst:.2e} of the parameter's gradient norm")
+
+
+def test_bf16_backward_design_within_reference_drift():
+    """The planned tensor-core training step (bf16 operands and bf16 incoming gradients in every
+    contraction, fp32 everywhere else — oracle/bf16_emulation.py) against the fp64 gradients: its drift must
+    not exceed the drift of the reference's OWN bf16-autocast step recorded in the golden fixture."""
+    import numpy as np
+    from helpers import GOLDEN
+    from oracle.bf16_emulation import emulate_bf16_gemms
+    name, (model_name, kind) = "grad_context_2spk_b2_t3000", ("context_2spk_b2_t3000", "tm_neg_sisnr")
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        ref_drift, ref_loss16, gold_loss = float(z["bf16_ref_global_rel_l2"]), float(z["bf16_ref_loss"]), float(z["loss"])
+    _, g_ref = _oracle_training_grads(model_name, kind)
+    with emulate_bf16_gemms():
+        loss16, g16 = _oracle_training_grads(model_name, kind)
+    num = sum(((g16[k] - g_ref[k]) ** 2).sum() for k in g_ref if g_ref[k] is not None)
+    den = sum((g_ref[k] ** 2).sum() for k in g_ref if g_ref[k] is not None)
+    drift = (num / den).sqrt().item()
+    print(f"bf16-GEMM emulation: loss {loss16:.4f} (fp32 {gold_loss:.4f}, reference autocast {ref_loss16:.4f}); "
+          f"gradient drift {drift:.3f} vs reference autocast drift {ref_drift:.3f}")
+    assert drift > 1e-4, "the emulation did not engage"
+    assert drift < 1.25 * ref_drift
+    assert abs(loss16 - gold_loss) < 1.25 * abs(ref_loss16 - gold_loss) + 0.05
