@@ -383,6 +383,16 @@ CSE_API int cse_mask_decode_bwd(const float* mask_pre, const float* E, const flo
 CSE_API int cse_encoder_bwd(const float* mix, const float* E, const float* dE, int B, int T,
                             float* d_w, void* stream);
 
+/* ---- EXPERIMENTAL (compiled, not yet run on hardware — see csrc/backward_tc.cu) ----
+ * nn.Linear backward on the tcgen05 GEMM: bf16 operands, fp32 accumulate.  A [M,K] float or bf16
+ * (a_is_bf16), W [N,K] fp32 master, dC [M,N] fp32 contiguous ->
+ *   dA [M,K] (fp32 if dA_fp32 else bf16; NULL to skip), dW [N,K] fp32 += , dbias [N] += .
+ * scratch: cse_linear_bwd_tc_scratch_bytes(M,N,K), 256-byte aligned. */
+CSE_API size_t cse_linear_bwd_tc_scratch_bytes(int M, int N, int K);
+CSE_API int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const float* dC,
+                              int M, int N, int K, void* dA, int dA_fp32, int ldda, float* dW,
+                              float* dbias, void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,48 @@
+"""GPU, EXPERIMENTAL: nn.Linear backward on the tcgen05 GEMM (csrc/backward_tc.cu).
+
+Written after the round's GPU budget was spent: the kernel composition has been compiled and
+argument-checked but never run on hardware, so this file is skipped unless CSE_EXPERIMENTAL=1 — it is the
+first thing to run next round.  Tolerance: bf16 operand rounding (2^-9 relative per element) against the
+fp64 closed form, i.e. ~4e-3 relative L2 for these reduction lengths.
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+import cse_b200  # noqa: F401
+from cse_b200 import _lib
+from helpers import rel_l2
+from oracle import backward_oracle as BO
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CSE_EXPERIMENTAL") != "1",
+                                 reason="not yet run on hardware; set CSE_EXPERIMENTAL=1")]
+DEV = "cuda:0"
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 256), (1000, 256, 1024), (5000, 1024, 256), (17068, 256, 256)])
+@pytest.mark.parametrize("a_bf16", [False, True])
+def test_linear_backward_tensor_core(M, N, K, a_bf16):
+    a, w, dc = _rand(M, K, seed=1), _rand(N, K, seed=2) / K ** 0.5, _rand(M, N, seed=3)
+    a_in = a.to(torch.bfloat16) if a_bf16 else a
+    da_ref, dw_ref, db_ref = BO.manual_linear_bwd(a_in.double(), w.double(), dc.double())
+    ad, wd, dcd = a_in.to(DEV), w.to(DEV), dc.to(DEV)
+    da = torch.empty(M, K, device=DEV)
+    dw, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    nbytes = _lib.load().cse_linear_bwd_tc_scratch_bytes(M, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.call("cse_linear_bwd_tc", _lib.ptr(ad), int(a_bf16), K, _lib.ptr(wd), _lib.ptr(dcd), M, N, K, _lib.ptr(da),
+              1, K, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), nbytes, st)
+    assert rel_l2(da.cpu(), da_ref) < 6e-3
+    assert rel_l2(dw.cpu(), dw_ref) < 6e-3
+    assert rel_l2(db.cpu(), db_ref) < 1e-4
+    _lib.call("cse_linear_bwd_tc", _lib.ptr(ad), int(a_bf16), K, _lib.ptr(wd), _lib.ptr(dcd), M, N, K, None,
+              1, K, _lib.ptr(dw), None, _lib.ptr(ws), nbytes, st)            # dW accumulates
+    assert rel_l2(dw.cpu(), 2 * dw_ref) < 6e-3

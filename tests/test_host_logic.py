@@ -177,3 +177,15 @@ def test_losses_and_training_refuse_cpu_tensors():
         losses.get_si_snr_with_pitwrapper(a, a)
     with pytest.raises(_lib.CseError):
         training.forward_train({}, torch.zeros(1, 4000), None, 2)
+
+
+def test_experimental_tensor_core_backward_entry_validates_arguments():
+    import ctypes as C
+    lib = _lib.load()
+    assert lib.cse_linear_bwd_tc_scratch_bytes(100, 256, 256) >= 100 * 256 * 2 + 256 * 256 * 6 + 2 * 256 * 128 * 2
+    assert lib.cse_linear_bwd_tc_scratch_bytes(0, 256, 256) == 0
+    p = C.c_void_p(0x1000)
+    with pytest.raises(_lib.CseError, match="multiples of 128"):
+        _lib.call("cse_linear_bwd_tc", p, 0, 256, p, p, 10, 200, 256, p, 1, 256, p, None, p, 1 << 30, None)
+    with pytest.raises(_lib.CseError, match="scratch too small"):
+        _lib.call("cse_linear_bwd_tc", p, 0, 256, p, p, 10, 256, 256, p, 1, 256, p, None, p, 16, None)
