@@ -14,9 +14,9 @@ SOURCES = ["abi.cu", "frontend.cu", "norm.cu", "gemm_simt.cu", "gemm_tc.cu", "at
            "attention_tc.cu", "gemm_ln_tc.cu", "ffn_tc.cu", "head.cu", "loss.cu", "backward.cu",
            "backward_abi.cu", "train_ops.cu", "backward_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# no --use_fast_math: the fp32 parity mode needs IEEE division / sqrt / expf
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
 def _stale(target, deps):
