@@ -104,6 +104,9 @@ _SIGNATURES = {
     "cse_linear_bwd_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "cse_linear_bwd_tc": (C.c_int, [_v, C.c_int, C.c_int, _v, _v, C.c_int, C.c_int, C.c_int, _v, C.c_int, C.c_int,
                                     _v, _v, _v, C.c_size_t, _v]),
+    "cse_layer_bwd_bf16_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "cse_layer_bwd_bf16": (C.c_int, [C.POINTER(LayerParams), C.POINTER(LayerGrads), _v, _v, C.c_int, C.c_int, _v,
+                                     C.c_size_t, _v]),
     "cse_layer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cse_layer_fwd": (C.c_int, [C.POINTER(LayerParams), _v, C.c_int, C.c_int, C.c_int, _v, C.c_size_t, _v]),
     "cse_layer_bwd": (C.c_int, [C.POINTER(LayerParams), C.POINTER(LayerGrads), _v, _v, C.c_int, C.c_int, _v,

@@ -6,10 +6,9 @@ train_ContExt.py:372-389).  Here each differentiable unit of the hot path is an
 `cse_*_si_snr` / `cse_*_si_snr_bwd`): PyTorch only carries the graph, the parameter ownership and
 the `.grad` buffers (so stock DDP gradient all-reduce applies unchanged).  No CPU / eager fallback.
 
-Built so far (fp32 parity mode): one pre-norm transformer layer (TransformerEncoderLayer.forward,
-CSE_transformer.py:385-416) with activation checkpointing at layer granularity, and the three
-SI-SNR losses (in losses.py).  The layer Function is what the 32-layer stacks are made of; the
-GroupNorm / chunking / head / encoder-decoder gradients are the next step.
+This module: one pre-norm transformer layer (TransformerEncoderLayer.forward, CSE_transformer.py:385-416)
+as an autograd node with activation checkpointing at layer granularity (fp32 parity mode).  The other
+stages and the composition of the whole forward live in training.py, the losses in losses.py.
 """
 import ctypes as C
 
@@ -62,19 +61,33 @@ def layer_forward(params, R, nseq, n):
     return out
 
 
-def layer_backward(params, R_in, dR_out, nseq, n, grads=None):
+def layer_backward(params, R_in, dR_out, nseq, n, grads=None, experimental_bf16=False):
     """Gradient of layer_forward: returns (dR_in, grads) with grads keyed like `params`.
-    `grads` may carry existing buffers to accumulate into (autograd .grad semantics)."""
+    `grads` may carry existing buffers to accumulate into (autograd .grad semantics).
+
+    experimental_bf16: route to cse_layer_bwd_bf16 (tensor-core recompute / dgrad / wgrad) — compiled but not
+    yet run on hardware (csrc/backward_tc.cu); nothing on the default path sets it."""
     _check(R_in, "R_in")
     _check(dR_out, "dR_out")
     if grads is None:
         grads = {key: torch.zeros_like(params[key]) for _, key in LAYER_KEYS}
     dR = dR_out.clone()
-    ws, nbytes = _workspace(nseq, n, R_in.device)
     lp = _layer_struct(params, _lib.LayerParams)
     lg = _layer_struct(grads, _lib.LayerGrads)
+    st = C.c_void_p(current_stream(R_in.device))
+    if experimental_bf16:
+        packs = {}
+        for field, key in LAYER_KEYS[:8:2]:                      # the four weight matrices
+            packs[field] = params[key].detach().to(torch.bfloat16).contiguous()
+            setattr(lp, field + "_bf16", C.c_void_p(packs[field].data_ptr()))
+        nbytes = _lib.load().cse_layer_bwd_bf16_workspace_bytes(nseq, n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=R_in.device)
+        _lib.call("cse_layer_bwd_bf16", C.byref(lp), C.byref(lg), _lib.ptr(R_in), _lib.ptr(dR), nseq, n,
+                  _lib.ptr(ws), nbytes, st)
+        return dR, grads
+    ws, nbytes = _workspace(nseq, n, R_in.device)
     _lib.call("cse_layer_bwd", C.byref(lp), C.byref(lg), _lib.ptr(R_in), _lib.ptr(dR), nseq, n, _lib.ptr(ws),
-              nbytes, C.c_void_p(current_stream(R_in.device)))
+              nbytes, st)
     return dR, grads
 
 

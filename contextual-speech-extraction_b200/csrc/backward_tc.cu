@@ -108,3 +108,135 @@ int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, con
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL, same status as above: one transformer layer backward in the performance mode —
+// bf16 recompute with the forward's own kernels (unfused FFN so that the hidden activation exists),
+// tensor-core dgrad / wgrad through cse_linear_bwd_tc, fp32 LayerNorm / attention / residual gradients.
+// ---------------------------------------------------------------------------------------------
+namespace cse {
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst,
+                                                          size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256)
+    st8(dst + i * 8, ld8(src + i * 8));
+}
+
+static int launch_bf16_to_f32(const bf16* src, float* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  const size_t n8 = n / 8;  // callers pass multiples of 256
+  const int grid = (int)min((size_t)148 * 8, (n8 + 255) / 256);
+  bf16_to_f32_kernel<<<grid, 256, 0, st>>>(src, dst, n8);
+  return check_launch("bf16_to_f32_kernel");
+}
+
+// d[i] = F[i] > 0 ? d[i] : 0 with the saved activation in bf16 and the gradient in fp32
+__global__ void __launch_bounds__(256) relu_bwd_mixed_kernel(const bf16* __restrict__ F, float* __restrict__ d,
+                                                             size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    const f8 f = ld8(F + i * 8);
+    f8 g = ld8(d + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = f.v[k] > 0.f ? g.v[k] : 0.f;
+    st8(d + i * 8, g);
+  }
+}
+
+static int launch_relu_bwd_mixed(const bf16* F, float* d, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  const size_t n8 = n / 8;
+  const int grid = (int)min((size_t)148 * 8, (n8 + 255) / 256);
+  relu_bwd_mixed_kernel<<<grid, 256, 0, st>>>(F, d, n8);
+  return check_launch("relu_bwd_mixed_kernel");
+}
+
+struct LayerWs16 {
+  bf16 *H, *QKV, *AO, *F1;
+  float *Rmid, *dBig, *dH, *QKV32, *AO32;
+  char* lin;          // scratch of cse_linear_bwd_tc, sized for the largest of the four linears
+  size_t lin_bytes, total;
+};
+
+static LayerWs16 carve_layer_ws16(char* ws, size_t M) {
+  LayerWs16 w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = ws ? ws + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return p;
+  };
+  w.H = (bf16*)take(M * kN * 2);
+  w.QKV = (bf16*)take(M * 3 * kN * 2);
+  w.AO = (bf16*)take(M * kN * 2);
+  w.F1 = (bf16*)take(M * kFfn * 2);
+  w.Rmid = (float*)take(M * kN * 4);
+  w.dBig = (float*)take(M * kFfn * 4);
+  w.dH = (float*)take(M * kN * 4);
+  w.QKV32 = (float*)take(M * 3 * kN * 4);
+  w.AO32 = (float*)take(M * kN * 4);
+  size_t lin = 0;
+  const size_t shapes[4][2] = {{(size_t)kN, (size_t)kFfn}, {(size_t)kFfn, (size_t)kN}, {(size_t)kN, (size_t)kN},
+                               {(size_t)3 * kN, (size_t)kN}};
+  for (auto& s : shapes) {
+    const size_t b = carve_tc_bwd(nullptr, M, s[0], s[1]).total;
+    if (b > lin) lin = b;
+  }
+  w.lin_bytes = lin;
+  w.lin = take(lin);
+  w.total = off;
+  return w;
+}
+
+}  // namespace cse
+
+extern "C" {
+
+size_t cse_layer_bwd_bf16_workspace_bytes(int nseq, int n) {
+  if (nseq <= 0 || n <= 0) return 0;
+  return carve_layer_ws16(nullptr, (size_t)nseq * n).total;
+}
+
+int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, const float* R_in, float* dR,
+                       int nseq, int n, void* workspace, size_t workspace_bytes, void* stream) {
+  CSE_REQUIRE(p && g && R_in && dR && workspace && nseq > 0 && n > 0, "layer_bwd_bf16: bad argument");
+  CSE_REQUIRE(p->in_proj_w_bf16 && p->out_proj_w_bf16 && p->ffn1_w_bf16 && p->ffn2_w_bf16,
+              "layer_bwd_bf16: bf16 weights missing (cse_pack_bf16)");
+  CSE_REQUIRE(((uintptr_t)workspace & 255) == 0, "layer_bwd_bf16: workspace must be 256-byte aligned");
+  CSE_REQUIRE((long long)nseq * n <= 2147483647LL / kFfn, "layer_bwd_bf16: %d x %d rows overflow the 32-bit tile index", nseq, n);
+  const int M = nseq * n;
+  const LayerWs16 w = carve_layer_ws16((char*)workspace, (size_t)M);
+  CSE_REQUIRE(workspace_bytes >= w.total, "layer_bwd_bf16: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row_bytes = (size_t)M * kN * sizeof(float);
+
+  // ---- recompute in the performance mode (the launch sequence of abi.cu:run_stack with the unfused FFN) ----
+  if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
+  if (launch_gemm_tc(w.H, kN, (const bf16*)p->in_proj_w_bf16, p->in_proj_b, 1.f, nullptr, w.QKV, 3 * kN, M, 3 * kN, kN, 0, 0, st)) return 1;
+  if (launch_attention(w.QKV, nseq, n, CSE_BF16, w.AO, st)) return 1;
+  CSE_CUDA(cudaMemcpyAsync(w.Rmid, R_in, row_bytes, cudaMemcpyDeviceToDevice, st));
+  if (launch_gemm_tc(w.AO, kN, (const bf16*)p->out_proj_w_bf16, p->out_proj_b, 1.f, w.Rmid, w.Rmid, kN, M, kN, kN, 0, 1, st)) return 1;
+  if (launch_layernorm(w.Rmid, p->ln2_g, p->ln2_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
+  if (launch_gemm_tc(w.H, kN, (const bf16*)p->ffn1_w_bf16, p->ffn1_b, 1.f, nullptr, w.F1, kFfn, M, kFfn, kN, 1, 0, st)) return 1;
+
+  // ---- FFN sub-block ----
+  if (cse_linear_bwd_tc(w.F1, 1, kFfn, p->ffn2_w, dR, M, kN, kFfn, w.dBig, 1, kFfn, g->ffn2_w, g->ffn2_b, w.lin,
+                        w.lin_bytes, stream)) return 1;
+  if (launch_relu_bwd_mixed(w.F1, w.dBig, (size_t)M * kFfn, st)) return 1;
+  if (cse_linear_bwd_tc(w.H, 1, kN, p->ffn1_w, w.dBig, M, kFfn, kN, w.dH, 1, kN, g->ffn1_w, g->ffn1_b, w.lin,
+                        w.lin_bytes, stream)) return 1;
+  if (launch_layernorm_bwd(w.Rmid, p->ln2_g, w.dH, M, 1e-6f, dR, 1, g->ln2_g, g->ln2_b, st)) return 1;
+
+  // ---- attention sub-block ----
+  if (cse_linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, dR, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
+                        w.lin_bytes, stream)) return 1;
+  if (launch_bf16_to_f32(w.QKV, w.QKV32, (size_t)M * 3 * kN, st)) return 1;
+  if (launch_bf16_to_f32(w.AO, w.AO32, (size_t)M * kN, st)) return 1;
+  float* dQKV = w.dBig;  // [M,768] fp32
+  if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
+  if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
+  if (cse_linear_bwd_tc(w.H, 1, kN, p->in_proj_w, dQKV, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
+                        w.lin_bytes, stream)) return 1;
+  return launch_layernorm_bwd(R_in, p->ln1_g, w.dH, M, 1e-6f, dR, 1, g->ln1_g, g->ln1_b, st);
+}
+
+}  // extern "C"

@@ -393,6 +393,14 @@ CSE_API int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float
                               int M, int N, int K, void* dA, int dA_fp32, int ldda, float* dW,
                               float* dbias, void* scratch, size_t scratch_bytes, void* stream);
 
+/* EXPERIMENTAL (same status): cse_layer_bwd in the performance mode — bf16 recompute with the forward's own
+ * tcgen05 kernels, tensor-core dgrad / wgrad, fp32 LayerNorm / attention / residual gradients.  p_host needs
+ * the *_bf16 members (cse_pack_bf16 layout: any bf16 copies of the four weight matrices). */
+CSE_API size_t cse_layer_bwd_bf16_workspace_bytes(int nseq, int n);
+CSE_API int cse_layer_bwd_bf16(const cse_layer_params* p_host, const cse_layer_grads* grads_host,
+                               const float* R_in, float* dR, int nseq, int n,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
