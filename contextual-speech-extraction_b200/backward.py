@@ -11,6 +11,7 @@ as an autograd node with activation checkpointing at layer granularity (fp32 par
 stages and the composition of the whole forward live in training.py, the losses in losses.py.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -25,6 +26,19 @@ LAYER_KEYS = (
     ("ln1_g", "norm1.norm.weight"), ("ln1_b", "norm1.norm.bias"),
     ("ln2_g", "norm2.norm.weight"), ("ln2_b", "norm2.norm.bias"),
 )
+
+
+# CSE_TRAIN_BF16=1: run the transformer layers of the TRAINING path in the performance mode (bf16 forward through
+# cse_layer_fwd, backward through the experimental cse_layer_bwd_bf16).  Unverified on hardware — off by default.
+EXPERIMENTAL_BF16 = os.environ.get("CSE_TRAIN_BF16") == "1"
+
+
+def _bf16_packs(params, lp):
+    packs = {}
+    for field, key in LAYER_KEYS[:8:2]:                          # the four weight matrices
+        packs[field] = params[key].detach().to(torch.bfloat16).contiguous()
+        setattr(lp, field + "_bf16", C.c_void_p(packs[field].data_ptr()))
+    return packs
 
 
 def _check(t, name):
@@ -48,16 +62,19 @@ def _workspace(nseq, n, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
-def layer_forward(params, R, nseq, n):
-    """TransformerEncoderLayer.forward in fp32 on the residual stream R [nseq*n, 256]; returns a new tensor."""
+def layer_forward(params, R, nseq, n, experimental_bf16=False):
+    """TransformerEncoderLayer.forward on the fp32 residual stream R [nseq*n, 256]; returns a new tensor.
+    fp32 arithmetic unless experimental_bf16 (the bench path's tensor-core launch sequence, one layer)."""
     _check(R, "R")
     if R.shape != (nseq * n, _lib.N):
         raise _lib.CseError(f"R has shape {tuple(R.shape)}, expected {(nseq * n, _lib.N)}")
     out = R.clone()
     ws, nbytes = _workspace(nseq, n, R.device)
     lp = _layer_struct(params, _lib.LayerParams)
-    _lib.call("cse_layer_fwd", C.byref(lp), _lib.ptr(out), nseq, n, _lib.FP32, _lib.ptr(ws), nbytes,
-              C.c_void_p(current_stream(R.device)))
+    packs = _bf16_packs(params, lp) if experimental_bf16 else None
+    _lib.call("cse_layer_fwd", C.byref(lp), _lib.ptr(out), nseq, n, _lib.BF16 if experimental_bf16 else _lib.FP32,
+              _lib.ptr(ws), nbytes, C.c_void_p(current_stream(R.device)))
+    del packs
     return out
 
 
@@ -76,10 +93,7 @@ def layer_backward(params, R_in, dR_out, nseq, n, grads=None, experimental_bf16=
     lg = _layer_struct(grads, _lib.LayerGrads)
     st = C.c_void_p(current_stream(R_in.device))
     if experimental_bf16:
-        packs = {}
-        for field, key in LAYER_KEYS[:8:2]:                      # the four weight matrices
-            packs[field] = params[key].detach().to(torch.bfloat16).contiguous()
-            setattr(lp, field + "_bf16", C.c_void_p(packs[field].data_ptr()))
+        packs = _bf16_packs(params, lp)  # noqa: F841  (kept alive until the call below is enqueued)
         nbytes = _lib.load().cse_layer_bwd_bf16_workspace_bytes(nseq, n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=R_in.device)
         _lib.call("cse_layer_bwd_bf16", C.byref(lp), C.byref(lg), _lib.ptr(R_in), _lib.ptr(dR), nseq, n,
@@ -99,14 +113,15 @@ class _LayerFn(torch.autograd.Function):
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
         ctx.save_for_backward(R, *weights)
         ctx.shape = (nseq, n)
-        return layer_forward(params, R.contiguous(), nseq, n)
+        return layer_forward(params, R.contiguous(), nseq, n, experimental_bf16=EXPERIMENTAL_BF16)
 
     @staticmethod
     def backward(ctx, dR_out):
         R, *weights = ctx.saved_tensors
         nseq, n = ctx.shape
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
-        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n)
+        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n,
+                                   experimental_bf16=EXPERIMENTAL_BF16)
         return (dR, None, None) + tuple(grads[key] for _, key in LAYER_KEYS)
 
 

@@ -25,3 +25,7 @@ echo "train N=1: exit $?"; cat gpurun_out/bench_train_n1.json
 #   ncu --metrics gpu__time_duration.sum --clock-control none -c 2100 --csv --log-file gpurun_out/launches_train.csv \
 #       python bench.py --workload train --steps 1 --warmup 3
 # and kill it after the first step (round 1 lost 7 GPU-minutes learning this).
+# 4. A/B of the experimental tensor-core layers inside the whole training step (only if step 1 passed):
+#   CSE_TRAIN_BF16=1 python bench.py --workload train --steps 5 --warmup 3
+#   CSE_TRAIN_BF16=1 CSE_EXPERIMENTAL=1 python -m pytest tests/test_training_gpu.py -k whole_model -s   (expect the fp32
+#   bounds to FAIL by design: compare the printed global rel-L2 with the reference's autocast drift 0.08-0.15)
