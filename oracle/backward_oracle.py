@@ -92,28 +92,41 @@ def manual_linear_bwd(a, w, dc):
     return dc @ w, dc2.t() @ a2, dc2.sum(0)
 
 
-def manual_layer_bwd(params, x, dy):
+def manual_layer_bwd(params, x, dy, rnd=None):
     """The launch sequence of cse_layer_bwd (csrc/backward_abi.cu): recompute, then walk back.
-    Returns (dx, {key -> grad})."""
+    Returns (dx, {key -> grad}).
+
+    rnd: optional rounding applied wherever the performance-mode composition (cse_layer_bwd_bf16,
+    csrc/backward_tc.cu) holds a bf16 value — stored activations (norm outputs, qkv, attention output, FFN
+    hidden), GEMM weight operands and the incoming gradient of every dgrad / wgrad; residual stream, LayerNorm and
+    attention gradients stay in full precision.  None = the fp32 parity path."""
     P = params
+    r = rnd if rnd is not None else (lambda t: t)
     g = {}
-    h1 = O.layer_norm(x, P["norm1.norm.weight"], P["norm1.norm.bias"])
-    qkv = h1 @ P["self_att.att.in_proj_weight"].t() + P["self_att.att.in_proj_bias"]
+
+    def lin_bwd(a, w, dc):                      # operands as the tensor-core GEMMs see them
+        return manual_linear_bwd(r(a), r(w), r(dc))
+
+    h1 = r(O.layer_norm(x, P["norm1.norm.weight"], P["norm1.norm.bias"]))
+    qkv = r(h1 @ r(P["self_att.att.in_proj_weight"]).t() + P["self_att.att.in_proj_bias"])
     ao, _ = manual_attention_bwd(qkv, torch.zeros_like(x))
-    rmid = x + ao @ P["self_att.att.out_proj.weight"].t() + P["self_att.att.out_proj.bias"]
-    h2 = O.layer_norm(rmid, P["norm2.norm.weight"], P["norm2.norm.bias"])
-    f1 = torch.relu(h2 @ P["pos_ffn.ffn.0.weight"].t() + P["pos_ffn.ffn.0.bias"])
+    ao = r(ao)
+    rmid = x + ao @ r(P["self_att.att.out_proj.weight"]).t() + P["self_att.att.out_proj.bias"]
+    h2 = r(O.layer_norm(rmid, P["norm2.norm.weight"], P["norm2.norm.bias"]))
+    f1 = r(torch.relu(h2 @ r(P["pos_ffn.ffn.0.weight"]).t() + P["pos_ffn.ffn.0.bias"]))
     dR = dy.clone()
-    df1, g["pos_ffn.ffn.3.weight"], g["pos_ffn.ffn.3.bias"] = manual_linear_bwd(f1, P["pos_ffn.ffn.3.weight"], dR)
+    df1, g["pos_ffn.ffn.3.weight"], g["pos_ffn.ffn.3.bias"] = lin_bwd(f1, P["pos_ffn.ffn.3.weight"], dR)
+    g["pos_ffn.ffn.3.bias"] = dR.reshape(-1, dR.shape[-1]).sum(0)           # bias gradients: fp32 column sums
     df1 = df1 * (f1 > 0)
-    dh2, g["pos_ffn.ffn.0.weight"], g["pos_ffn.ffn.0.bias"] = manual_linear_bwd(h2, P["pos_ffn.ffn.0.weight"], df1)
+    dh2, g["pos_ffn.ffn.0.weight"], _ = lin_bwd(h2, P["pos_ffn.ffn.0.weight"], df1)
+    g["pos_ffn.ffn.0.bias"] = df1.reshape(-1, df1.shape[-1]).sum(0)
     dx2, g["norm2.norm.weight"], g["norm2.norm.bias"] = manual_layernorm_bwd(rmid, P["norm2.norm.weight"], dh2)
     dR = dR + dx2
-    dao, g["self_att.att.out_proj.weight"], g["self_att.att.out_proj.bias"] = \
-        manual_linear_bwd(ao, P["self_att.att.out_proj.weight"], dR)
+    dao, g["self_att.att.out_proj.weight"], _ = lin_bwd(ao, P["self_att.att.out_proj.weight"], dR)
+    g["self_att.att.out_proj.bias"] = dR.reshape(-1, dR.shape[-1]).sum(0)
     _, dqkv = manual_attention_bwd(qkv, dao)
-    dh1, g["self_att.att.in_proj_weight"], g["self_att.att.in_proj_bias"] = \
-        manual_linear_bwd(h1, P["self_att.att.in_proj_weight"], dqkv)
+    dh1, g["self_att.att.in_proj_weight"], _ = lin_bwd(h1, P["self_att.att.in_proj_weight"], dqkv)
+    g["self_att.att.in_proj_bias"] = dqkv.reshape(-1, dqkv.shape[-1]).sum(0)
     dx1, g["norm1.norm.weight"], g["norm1.norm.bias"] = manual_layernorm_bwd(x, P["norm1.norm.weight"], dh1)
     return dR + dx1, g
 

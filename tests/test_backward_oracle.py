@@ -180,3 +180,20 @@ def test_bf16_backward_design_within_reference_drift():
     assert drift > 1e-4, "the emulation did not engage"
     assert drift < 1.25 * ref_drift
     assert abs(loss16 - gold_loss) < 1.25 * abs(ref_loss16 - gold_loss) + 0.05
+
+
+def test_performance_mode_layer_backward_tolerance_is_reachable():
+    """Numerical model of cse_layer_bwd_bf16 (bf16 wherever that composition stores or multiplies bf16 values)
+    against the fp64 gradients: sets the bound of tests/test_backward_tc_gpu.py before it has run (one layer at
+    bf16 moves its gradients by 2-5 %; 32 of them give the 0.12 whole-model drift of the test above)."""
+    p = _layer_params(71)
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(3, 251, 256, generator=g).double()
+    dy = torch.randn(3, 251, 256, generator=g).double()
+    _, dx_ref, g_ref = BO.autograd_layer(p, x, dy)
+    rnd = lambda t: t.to(torch.bfloat16).to(t.dtype)
+    dx, grads = BO.manual_layer_bwd(p, x, dy, rnd=rnd)
+    errs = {k: rel_l2(grads[k], g_ref[k]) for k in BO.LAYER_KEYS}
+    errs["dx"] = rel_l2(dx, dx_ref)
+    print("bf16 layer-backward model, rel-L2 per gradient:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert 1e-4 < max(errs.values()) < 6e-2            # engaged, and inside the GPU test's 8e-2 bound
