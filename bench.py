@@ -124,15 +124,16 @@ def run_reference(args):
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     if getattr(args, "workload", "forward") == "train":
-        value, per_step, cores = cpu_train_rate(steps, warmup)
-        sample = (f"1 mixture x {SECONDS} s forward + -SI-SNR + backward under autograd per step ({steps} timed steps, "
+        value, per_step, cores = cpu_train_rate(steps, warmup, args.train_seconds, args.train_loss)
+        sample = (f"1 mixture x {args.train_seconds} s forward + loss ({args.train_loss}) + backward under autograd per step ({steps} timed steps, "
                   f"{warmup} warm-up), fp32, oracle port of the reference modules")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ContExt 2-spk forward+backward (BASELINE.json configs[2]); bounded sample: 1 of the 2 mixtures per step, no optimizer step",
-                       "batch_per_step": 1, "seconds": SECONDS, "sample_rate": SR, "ctx_tokens": CTX_TOKENS},
+                       "batch_per_step": 1, "seconds": args.train_seconds, "sample_rate": SR, "ctx_tokens": CTX_TOKENS,
+                       "loss": args.train_loss},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -332,28 +333,34 @@ def run_ours(args):
 TRAIN_BATCH = 2
 
 
-def cpu_train_rate(steps, warmup):
-    """Oracle port, forward + backward of the ContExt loss under autograd, one mixture per step."""
+def cpu_train_rate(steps, warmup, seconds=SECONDS, loss_kind="sisnr"):
+    """Oracle port, forward + backward of the training loss under autograd, one mixture per step."""
     import torch
     import cse_b200  # noqa: F401
     from cse_b200 import synth
     from oracle import sepformer_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    variant = "contsep" if loss_kind == "pit" else "context"
     sd = {k: (v.requires_grad_(True) if "pos_enc" not in k else v)
-          for k, v in synth.make_state_dict("context", SPK, seed=0).items()}
-    mix, src = synth.make_mixture(1, T, SPK, seed=1234)
+          for k, v in synth.make_state_dict(variant, SPK, seed=0).items()}
+    mix, src = synth.make_mixture(1, seconds * SR, SPK, seed=1234)
     ctx = synth.make_context(1, CTX_TOKENS, seed=1234)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        est = O.sepformer_forward(sd, mix, ctx, "context", SPK)
-        loss = -O.tm_si_snr(est[:, :, 0], src[:, :, 0]).mean()
+        if loss_kind == "pit":
+            est, pred = O.sepformer_forward(sd, mix, ctx, "contsep", SPK)
+            pit, _ = O.pit_si_snr(est, src)
+            loss = pit.mean() + torch.nn.functional.cross_entropy(pred, torch.zeros(1, dtype=torch.long))
+        else:
+            est = O.sepformer_forward(sd, mix, ctx, "context", SPK)
+            loss = -O.tm_si_snr(est[:, :, 0], src[:, :, 0]).mean()
         loss.backward()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
-    return SECONDS / per_step, per_step, cores
+    return seconds / per_step, per_step, cores
 
 
 def run_train(args):
@@ -363,7 +370,10 @@ def run_train(args):
     import cse_b200  # noqa: F401
     from cse_b200 import _lib, losses, shapes, synth
     from cse_b200.models.ContExt import Sepformer
+    from cse_b200.models.ContSep import Sepformer as ContSep
 
+    seconds, loss_kind = args.train_seconds, args.train_loss
+    Tt = seconds * SR
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -376,9 +386,14 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    model = Sepformer(SPK, add_ctx=True)
-    model.add_ctx_pipeline()
-    model.load_state_dict(synth.make_state_dict("context", SPK, seed=0))
+    if loss_kind == "pit":       # train_ContSep.py: PIT SI-SNR + cross-entropy on the context selector
+        model = ContSep(SPK, add_mt=True)
+        model.add_mt_pipeline()
+        model.load_state_dict(synth.make_state_dict("contsep", SPK, seed=0))
+    else:                        # train_ContExt.py: -SI-SNR of the extracted stream
+        model = Sepformer(SPK, add_ctx=True)
+        model.add_ctx_pipeline()
+        model.load_state_dict(synth.make_state_dict("context", SPK, seed=0))
     model = model.to(dev).train()
     model.precision = "fp32"
     net = model
@@ -387,16 +402,22 @@ def run_train(args):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, amsgrad=True)      # train_ContSep.py:233
     sisnr = losses.ScaleInvariantSignalNoiseRatio()
 
-    mix_h, src_h = synth.make_mixture(TRAIN_BATCH, T, SPK, seed=4321 + rank)
+    mix_h, src_h = synth.make_mixture(TRAIN_BATCH, Tt, SPK, seed=4321 + rank)
     ctx_h = synth.make_context(TRAIN_BATCH, CTX_TOKENS, seed=4321 + rank)
-    tgt_h = src_h[:, :, 0].contiguous().pin_memory()
+    tgt_h = (src_h if loss_kind == "pit" else src_h[:, :, 0]).contiguous().pin_memory()
+    label = torch.zeros(TRAIN_BATCH, dtype=torch.long, device=dev)
     mix_h, ctx_h = mix_h.pin_memory(), ctx_h.pin_memory()
     mix_d, ctx_d, tgt_d = mix_h.to(dev), ctx_h.to(dev), tgt_h.to(dev)
 
     def step(mix, ctx, tgt):
         opt.zero_grad(set_to_none=True)
-        est = net(mix, ctx)
-        loss = -sisnr(est[:, :, 0], tgt)                                    # train_ContExt.py:366-367
+        if loss_kind == "pit":
+            est, pred = net(mix, ctx)
+            loss = (losses.get_si_snr_with_pitwrapper(est, tgt).mean()       # train_ContSep.py:391-394
+                    + torch.nn.functional.cross_entropy(pred, label))
+        else:
+            est = net(mix, ctx)
+            loss = -sisnr(est[:, :, 0], tgt)                                # train_ContExt.py:366-367
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)             # train_ContSep.py:411
         opt.step()
@@ -447,7 +468,7 @@ def run_train(args):
     launches = lib.cse_launch_count() - n0
     ms_total, _ = timed(step_device, args.steps)
     ms_step = ms_total / args.steps
-    audio_s = TRAIN_BATCH * SECONDS * world
+    audio_s = TRAIN_BATCH * seconds * world
     value = audio_s / (ms_step / 1e3)
     _, wall = timed(step_host, args.steps)
     e2e_value = audio_s / (wall / args.steps)
@@ -455,7 +476,7 @@ def run_train(args):
 
     roofline = cpu = None
     if rank == 0:
-        ps = shapes.path_shape(TRAIN_BATCH, T, CTX_TOKENS, 1)
+        ps = shapes.path_shape(TRAIN_BATCH, Tt, CTX_TOKENS, SPK if loss_kind == "pit" else 1)
         peaks = load_peaks()
         # forward + recomputed forward (layer checkpointing) + dgrad + wgrad = 4x the forward contractions
         flops = 4.0 * shapes.algorithmic_flops(ps)
@@ -466,20 +487,22 @@ def run_train(args):
                     "traffic": None,
                     "note": "fp32 SIMT kernels: this fraction is against the bf16 tensor peak the tcgen05 backward will be held to"}
         if world == 1:
-            v, per_step, cores = cpu_train_rate(2, 1)
+            v, per_step, cores = cpu_train_rate(2, 1, seconds, loss_kind)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1 mixture ({SECONDS} s) forward+backward per step under autograd, 2 timed steps + 1 warm-up, fp32 oracle port, {cores} threads"}
+                   "sample": f"1 mixture ({seconds} s) forward+backward per step under autograd, 2 timed steps + 1 warm-up, fp32 oracle port, {cores} threads"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ContExt 2-spk forward + -SI-SNR loss + backward + grad all-reduce + clip + AdamW (BASELINE.json configs[2])",
-                       "batch_per_gpu": TRAIN_BATCH, "seconds": SECONDS, "sample_rate": SR, "ctx_tokens": CTX_TOKENS,
+            "config": {"workload": ("ContSep 2-spk forward + PIT SI-SNR + selector CE" if loss_kind == "pit" else
+                                    "ContExt 2-spk forward + -SI-SNR loss")
+                       + " + backward + grad all-reduce + clip + AdamW (BASELINE.json configs[2])",
+                       "batch_per_gpu": TRAIN_BATCH, "seconds": seconds, "sample_rate": SR, "ctx_tokens": CTX_TOKENS,
                        "num_spks": SPK, "weights": "random-init (seeded)",
                        "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
                        "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TRAIN_BATCH * (2 * T + CTX_TOKENS * 4096) * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() + ctx_h.numel() + tgt_h.numel()) * 4,
                     "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }), flush=True)
@@ -495,6 +518,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
                     help="forward = BASELINE configs[1] (the driver's contract); train = configs[2]")
+    ap.add_argument("--train-seconds", type=int, default=SECONDS, help="--workload train: mixture length (4; 16 = max_sp_len cap)")
+    ap.add_argument("--train-loss", default="sisnr", choices=["sisnr", "pit"],
+                    help="--workload train: ContExt -SI-SNR (train_ContExt.py:367) or ContSep PIT + selector CE (train_ContSep.py:391-394)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,9 +18,13 @@ timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > g
 echo "pytest -m gpu: exit $?"; tail -3 gpurun_out/t_all.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 echo "smoke: exit $?"; tail -3 gpurun_out/smoke.log
-# 3. training step: 4 s and the 16 s max_sp_len cap are separate runs of the same command (edit SECONDS in bench.py)
+# 3. training step (SURVEY §8d cfg 3): fixed 4 s with the ContExt loss, then the PIT variant and the 16 s max_sp_len cap
 timeout 200 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/bench_train_n1.json 2> gpurun_out/bench_train_n1.err
 echo "train N=1: exit $?"; cat gpurun_out/bench_train_n1.json
+timeout 200 python bench.py --workload train --train-loss pit --steps 5 --warmup 3 > gpurun_out/bench_train_pit_n1.json 2>> gpurun_out/bench_train_n1.err
+echo "train PIT: exit $?"; cat gpurun_out/bench_train_pit_n1.json
+timeout 300 python bench.py --workload train --train-seconds 16 --steps 3 --warmup 3 > gpurun_out/bench_train_16s_n1.json 2>> gpurun_out/bench_train_n1.err
+echo "train 16 s: exit $?"; cat gpurun_out/bench_train_16s_n1.json
 # NOTE: an ncu launch list of the training bench costs ~0.2 s per launch (2000 launches per step): capture ONE step,
 #   ncu --metrics gpu__time_duration.sum --clock-control none -c 2100 --csv --log-file gpurun_out/launches_train.csv \
 #       python bench.py --workload train --steps 1 --warmup 3
