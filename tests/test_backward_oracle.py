@@ -197,3 +197,27 @@ def test_performance_mode_layer_backward_tolerance_is_reachable():
     errs["dx"] = rel_l2(dx, dx_ref)
     print("bf16 layer-backward model, rel-L2 per gradient:", {k: f"{v:.1e}" for k, v in errs.items()})
     assert 1e-4 < max(errs.values()) < 6e-2            # engaged, and inside the GPU test's 8e-2 bound
+
+
+def test_tensor_core_linear_backward_dataflow():
+    """Index algebra of cse_linear_bwd_tc (csrc/backward_tc.cu), replayed with the semantics of its building
+    blocks — gemm_tc(A, W) = A W^T over K-contiguous operands, transposing casts zero-padded to Mpad — against the
+    closed form.  (Numerics aside: this is about which matrix is transposed where.)"""
+    M, N, K = 70, 256, 128
+    g = torch.Generator().manual_seed(5)
+    a, w, dc = (torch.randn(M, K, generator=g).double(), torch.randn(N, K, generator=g).double(),
+                torch.randn(M, N, generator=g).double())
+    da_ref, dw_ref, _ = BO.manual_linear_bwd(a, w, dc)
+    gemm_tc = lambda A, W: A @ W.t()                       # C[M,N] = A[M,K] W[N,K]^T
+
+    def transpose_cast(X, Mpad):                           # [M,n] -> [n,Mpad], zero padded
+        out = torch.zeros(X.shape[1], Mpad, dtype=X.dtype)
+        out[:, : X.shape[0]] = X.t()
+        return out
+
+    Mpad = (M + 63) // 64 * 64
+    wt = w.t().contiguous()                                # launch_transpose(W, N, K) -> [K,N]
+    da = gemm_tc(dc, wt)                                   # (M, N_gemm=K, K_gemm=N)
+    dw = gemm_tc(transpose_cast(dc, Mpad), transpose_cast(a, Mpad))   # (M_gemm=N, N_gemm=K, K_gemm=Mpad)
+    assert da.shape == (M, K) and dw.shape == (N, K)
+    assert rel_l2(da, da_ref) < 1e-12 and rel_l2(dw, dw_ref) < 1e-12
