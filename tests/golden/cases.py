@@ -35,3 +35,28 @@ GRAD_CASES = {
     "grad_contsep_2spk_bce_b1_t2024": ("contsep_2spk_bce_b1_t2024", "pit_plus_sel"),
 }
 GRAD_HEAD = 64
+
+# BASELINE.json shapes (make_golden_baseline.py; tests/test_baseline_shapes_gpu.py).  `batch`/`index`: the case is
+# item `index` of a seeded batch of `batch` mixtures (the bench.py batch for cfg 2), run alone at B=1.
+BASELINE_CASES = {
+    # configs[1]: ContSep 2-spk, 16 x 4 s, c = 1 — bench.py's own batch (weights seed 0, inputs seed 1234), items 0 and 15
+    "baseline_cfg2_mix0": dict(variant="contsep", spk=2, c=1, T=32000, cue=None, wseed=0, iseed=1234, batch=16, index=0),
+    "baseline_cfg2_mix15": dict(variant="contsep", spk=2, c=1, T=32000, cue=None, wseed=0, iseed=1234, batch=16, index=15),
+    # configs[3]: H-ContExt 3-spk, 16 s (max_sp_len), ctx + speaker token (c = 2): intra n = 252, inter n = 132
+    "baseline_cfg4_hcontext_3spk_16s": dict(variant="hcontext", spk=3, c=1, T=128000, cue="joint", wseed=40, iseed=41,
+                                           batch=1, index=0),
+    # 32 s: inter n = 259 > 256 — the attention path beyond the tcgen05 kernel's whole-row-in-TMEM limit
+    "baseline_32s_contsep_2spk": dict(variant="contsep", spk=2, c=1, T=256000, cue=None, wseed=42, iseed=43,
+                                     batch=1, index=0, window=16000),
+}
+
+
+def baseline_inputs(case):
+    """(mix [1,T], src [1,T,spk], ctx [1,c,4096], se [1,1,192] | None) of a BASELINE_CASES entry."""
+    from cse_b200 import synth
+    B, i = case["batch"], case["index"]
+    mix, src = synth.make_mixture(B, case["T"], max(case["spk"], 2), seed=case["iseed"])
+    ctx = synth.make_context(B, case["c"], seed=case["iseed"])
+    se = synth.make_speaker_embedding(B, seed=case["iseed"]) if case["variant"] == "hcontext" else None
+    sl = slice(i, i + 1)
+    return mix[sl].contiguous(), src[sl].contiguous(), ctx[sl].contiguous(), (None if se is None else se[sl].contiguous())

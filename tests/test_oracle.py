@@ -92,3 +92,27 @@ def test_oracle_matches_live_reference(name):
     est, pred = _run_oracle(sd, mix, ctx, se, meta)
     assert rel_l2(est, r_est) < 2e-5
     assert rel_l2(r_est, load_golden(name)["est"]) < 1e-6     # fixtures are reproducible
+
+
+@pytest.mark.parametrize("name", ["baseline_cfg2_mix0", "baseline_cfg2_mix15", "baseline_cfg4_hcontext_3spk_16s",
+                                  "baseline_32s_contsep_2spk"])
+def test_oracle_matches_reference_at_baseline_shapes(name):
+    """The pin at the BASELINE.json shapes themselves (cfg 2 items of bench.py's batch, cfg 4 = 16 s 3-spk c = 2,
+    32 s): fixtures written by tests/golden/make_golden_baseline.py from the reference's own modules."""
+    from cases import BASELINE_CASES, baseline_inputs
+    from cse_b200 import synth
+    case = BASELINE_CASES[name]
+    mix, src, ctx, se = baseline_inputs(case)
+    sd = synth.make_state_dict(case["variant"], case["spk"], seed=case["wseed"])
+    with torch.no_grad():
+        out = O.sepformer_forward(sd, mix, ctx, case["variant"], case["spk"], se=se, cue=case["cue"] or "joint")
+    est, pred = out if isinstance(out, tuple) else (out, None)
+    fix = load_golden(name)
+    if "win" in fix:
+        w = int(fix["win"])
+        assert rel_l2(est[:, :w], fix["est_head"]) < 2e-5 and rel_l2(est[:, -w:], fix["est_tail"]) < 2e-5
+        assert abs(est.double().norm().item() / float(fix["est_norm"]) - 1) < 1e-5
+    else:
+        assert est.shape == fix["est"].shape and rel_l2(est, fix["est"]) < 2e-5
+    if pred is not None:
+        assert rel_l2(pred, fix["context_pred"]) < 2e-5
