@@ -66,6 +66,11 @@ _SIGNATURES = {
     "cse_pack_bf16": (C.c_int, [C.POINTER(Params), C.c_int, _v, C.c_size_t, _v]),
     "cse_forward": (C.c_int, [C.POINTER(Params), _v, _v] + [C.c_int] * 5 + [_v, _v, _v, C.c_size_t, _v]),
     "cse_forward_host": (C.c_int, [C.POINTER(Params), _v, _v] + [C.c_int] * 5 + [_v, _v, _v, C.c_size_t, _v]),
+    "cse_pipeline_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "cse_pipeline_create": (C.c_int, [C.POINTER(Params)] + [C.c_int] * 6 + [_v, C.c_size_t, C.POINTER(_v)]),
+    "cse_pipeline_submit": (C.c_int, [_v, _v, _v, _v, _v, C.POINTER(C.c_int)]),
+    "cse_pipeline_wait": (C.c_int, [_v, C.c_int]),
+    "cse_pipeline_destroy": (C.c_int, [_v]),
     "cse_masknet_fwd": (C.c_int, [C.POINTER(Params), _v, _v] + [C.c_int] * 5 + [_v, _v, _v, C.c_size_t, _v]),
     "cse_encoder_fwd": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v, C.POINTER(C.c_int), _v]),
     "cse_gn_finalize": (C.c_int, [_v, C.c_int, C.c_int, C.c_double, C.c_float, _v, _v]),

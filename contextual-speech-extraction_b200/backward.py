@@ -28,9 +28,19 @@ LAYER_KEYS = (
 )
 
 
-# CSE_TRAIN_BF16=1: run the transformer layers of the TRAINING path in the performance mode (bf16 forward through
-# cse_layer_fwd, backward through the experimental cse_layer_bwd_bf16).  Unverified on hardware — off by default.
-EXPERIMENTAL_BF16 = os.environ.get("CSE_TRAIN_BF16") == "1"
+# Performance-mode training layers (bf16 tensor-core forward through cse_layer_fwd, backward through
+# cse_layer_bwd_bf16): used when the training step runs under torch.autocast (the reference's --fp16 / --bf16
+# switch, train_ContSep.py:383).  CSE_TRAIN_BF16=0 forces the fp32 parity kernels even under autocast,
+# CSE_TRAIN_BF16=1 forces the tensor-core layers even without autocast (A/B aid).
+_ENV_BF16 = os.environ.get("CSE_TRAIN_BF16")
+
+
+def use_bf16_layers(autocast_bf16):
+    if _ENV_BF16 == "1":
+        return True
+    if _ENV_BF16 == "0":
+        return False
+    return bool(autocast_bf16)
 
 
 def _bf16_packs(params, lp):
@@ -109,22 +119,22 @@ class _LayerFn(torch.autograd.Function):
     """One transformer layer as an autograd node: saves only its input (checkpointing)."""
 
     @staticmethod
-    def forward(ctx, R, nseq, n, *weights):
+    def forward(ctx, R, nseq, n, bf16, *weights):
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
         ctx.save_for_backward(R, *weights)
-        ctx.shape = (nseq, n)
-        return layer_forward(params, R.contiguous(), nseq, n, experimental_bf16=EXPERIMENTAL_BF16)
+        ctx.shape = (nseq, n, bool(bf16))
+        return layer_forward(params, R.contiguous(), nseq, n, experimental_bf16=bool(bf16))
 
     @staticmethod
     def backward(ctx, dR_out):
         R, *weights = ctx.saved_tensors
-        nseq, n = ctx.shape
+        nseq, n, bf16 = ctx.shape
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
-        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n,
-                                   experimental_bf16=EXPERIMENTAL_BF16)
-        return (dR, None, None) + tuple(grads[key] for _, key in LAYER_KEYS)
+        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n, experimental_bf16=bf16)
+        return (dR, None, None, None) + tuple(grads[key] for _, key in LAYER_KEYS)
 
 
-def transformer_layer(params, R, nseq, n):
-    """Differentiable fp32 transformer layer: R [nseq*n,256] -> same, gradients by cse_layer_bwd."""
-    return _LayerFn.apply(R, nseq, n, *[params[key] for _, key in LAYER_KEYS])
+def transformer_layer(params, R, nseq, n, bf16=False):
+    """Differentiable transformer layer: R [nseq*n,256] fp32 -> same; fp32 parity kernels (cse_layer_bwd) or, with
+    bf16=True, the tensor-core forward / recompute / dgrad / wgrad (cse_layer_bwd_bf16)."""
+    return _LayerFn.apply(R, nseq, n, use_bf16_layers(bf16), *[params[key] for _, key in LAYER_KEYS])

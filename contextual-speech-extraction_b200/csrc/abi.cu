@@ -464,6 +464,162 @@ int cse_forward_host(const cse_params* p, const float* mix_host, const float* ct
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined host entry: `depth` forwards in flight.  Slot i owns a full workspace (incl. the device
+// staging of its inputs / outputs) and a CUDA graph of forward_impl captured on it; three streams
+// (H2D, forward, D2H) chained by events, so the copy-in of step i+1 and the copy-out of step i-1
+// overlap the forward of step i and the ~220 launches of a forward replay as one graph launch.
+// Reference call site: the eval loop `model(mix.cuda(), ctx)` ... `.cpu()` per batch (test.py:231-245).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPipeDepth = 8;
+
+struct PipeSlot {
+  char* ws = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaEvent_t h2d = nullptr, fwd = nullptr, d2h = nullptr;
+  bool in_flight = false;
+};
+
+}  // extern "C"
+
+struct cse_pipeline {
+  cse::Plan pl;
+  int depth = 0, next = 0;
+  bool has_pred = false;
+  cudaStream_t s_in = nullptr, s_fw = nullptr, s_out = nullptr;
+  PipeSlot slot[kMaxPipeDepth];
+};
+
+static void pipeline_free(cse_pipeline* q) {
+  if (q == nullptr) return;
+  for (int i = 0; i < q->depth; ++i) {
+    PipeSlot& s = q->slot[i];
+    if (s.d2h && s.in_flight) cudaEventSynchronize(s.d2h);
+    if (s.exec) cudaGraphExecDestroy(s.exec);
+    if (s.h2d) cudaEventDestroy(s.h2d);
+    if (s.fwd) cudaEventDestroy(s.fwd);
+    if (s.d2h) cudaEventDestroy(s.d2h);
+  }
+  if (q->s_in) cudaStreamDestroy(q->s_in);
+  if (q->s_fw) cudaStreamDestroy(q->s_fw);
+  if (q->s_out) cudaStreamDestroy(q->s_out);
+  delete q;
+}
+
+extern "C" {
+
+size_t cse_pipeline_workspace_bytes(int B, int T, int c, int n_masks, int precision, int depth) {
+  Plan pl;
+  if (depth < 1 || depth > kMaxPipeDepth || make_plan(B, T, c, n_masks, precision, &pl)) return 0;
+  return align_up(pl.total, 256) * (size_t)depth;
+}
+
+int cse_pipeline_create(const cse_params* p, int B, int T, int c, int n_masks, int precision, int depth,
+                        void* workspace, size_t workspace_bytes, cse_pipeline** out) {
+  CSE_REQUIRE(p && workspace && out, "pipeline_create: NULL argument");
+  CSE_REQUIRE(depth >= 1 && depth <= kMaxPipeDepth, "pipeline_create: depth %d outside [1,%d]", depth, kMaxPipeDepth);
+  CSE_REQUIRE(((uintptr_t)workspace & 255) == 0, "pipeline_create: workspace must be 256-byte aligned");
+  cse_pipeline* q = new cse_pipeline();
+  if (make_plan(B, T, c, n_masks, precision, &q->pl)) { delete q; return 1; }
+  const size_t per_slot = align_up(q->pl.total, 256);
+  if (workspace_bytes < per_slot * depth) {
+    set_error("pipeline_create: workspace too small (%zu < %zu bytes)", workspace_bytes, per_slot * depth);
+    delete q;
+    return 1;
+  }
+  q->depth = depth;
+  q->has_pred = c > 0;
+  auto fail = [&](const char* what, cudaError_t e) {
+    set_error("pipeline_create: %s failed: %s", what, cudaGetErrorString(e));
+    pipeline_free(q);
+    return 1;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&q->s_fw, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+  const Plan& pl = q->pl;
+  for (int i = 0; i < depth; ++i) {
+    PipeSlot& s = q->slot[i];
+    s.ws = (char*)workspace + per_slot * i;
+    if ((e = cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.fwd, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    float* d_mix = (float*)(s.ws + pl.h_mix);
+    float* d_ctx = c > 0 ? (float*)(s.ws + pl.h_ctx) : nullptr;
+    float* d_est = (float*)(s.ws + pl.h_est);
+    float* d_pred = q->has_pred ? (float*)(s.ws + pl.h_pred) : nullptr;
+    // inputs of the warm-up run must be finite: zero them
+    if ((e = cudaMemsetAsync(d_mix, 0, (size_t)B * T * 4, q->s_fw)) != cudaSuccess) return fail("memset", e);
+    if (c > 0 && (e = cudaMemsetAsync(d_ctx, 0, (size_t)B * c * CSE_CTX * 4, q->s_fw)) != cudaSuccess)
+      return fail("memset", e);
+    // warm-up outside capture: one-time function attributes and tensor-map encodes happen here
+    if (forward_impl(p, d_mix, d_ctx, pl, d_est, d_pred, s.ws, q->s_fw)) { pipeline_free(q); return 1; }
+    if ((e = cudaStreamSynchronize(q->s_fw)) != cudaSuccess) return fail("warm-up forward", e);
+    if ((e = cudaStreamBeginCapture(q->s_fw, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+      return fail("cudaStreamBeginCapture", e);
+    const int rc = forward_impl(p, d_mix, d_ctx, pl, d_est, d_pred, s.ws, q->s_fw);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(q->s_fw, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      pipeline_free(q);
+      return 1;
+    }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture", e);
+    e = cudaGraphInstantiate(&s.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate", e);
+  }
+  *out = q;
+  return 0;
+}
+
+int cse_pipeline_submit(cse_pipeline* q, const float* mix_host, const float* ctx_host, float* est_host,
+                        float* pred_head_host, int* slot_out) {
+  CSE_REQUIRE(q && mix_host && est_host, "pipeline_submit: NULL argument");
+  const Plan& pl = q->pl;
+  const cse_shape& sh = pl.sh;
+  CSE_REQUIRE(sh.c == 0 || ctx_host != nullptr, "pipeline_submit: c=%d but ctx is NULL", sh.c);
+  CSE_REQUIRE(pred_head_host == nullptr || q->has_pred, "pipeline_submit: pred_head needs c > 0");
+  const int i = q->next;
+  PipeSlot& s = q->slot[i];
+  if (s.in_flight) {  // the slot's previous result has not been collected: wait for it (keeps the depth bounded)
+    CSE_CUDA(cudaEventSynchronize(s.d2h));
+    s.in_flight = false;
+  }
+  CSE_CUDA(cudaMemcpyAsync(s.ws + pl.h_mix, mix_host, (size_t)sh.B * sh.T * 4, cudaMemcpyHostToDevice, q->s_in));
+  if (sh.c > 0)
+    CSE_CUDA(cudaMemcpyAsync(s.ws + pl.h_ctx, ctx_host, (size_t)sh.B * sh.c * CSE_CTX * 4, cudaMemcpyHostToDevice, q->s_in));
+  CSE_CUDA(cudaEventRecord(s.h2d, q->s_in));
+  CSE_CUDA(cudaStreamWaitEvent(q->s_fw, s.h2d, 0));
+  CSE_CUDA(cudaGraphLaunch(s.exec, q->s_fw));
+  CSE_CUDA(cudaEventRecord(s.fwd, q->s_fw));
+  CSE_CUDA(cudaStreamWaitEvent(q->s_out, s.fwd, 0));
+  CSE_CUDA(cudaMemcpyAsync(est_host, s.ws + pl.h_est, (size_t)sh.B * sh.T * pl.n_masks * 4, cudaMemcpyDeviceToHost, q->s_out));
+  if (pred_head_host)
+    CSE_CUDA(cudaMemcpyAsync(pred_head_host, s.ws + pl.h_pred, (size_t)sh.B * kN * 4, cudaMemcpyDeviceToHost, q->s_out));
+  CSE_CUDA(cudaEventRecord(s.d2h, q->s_out));
+  s.in_flight = true;
+  q->next = (i + 1) % q->depth;
+  if (slot_out) *slot_out = i;
+  return 0;
+}
+
+int cse_pipeline_wait(cse_pipeline* q, int slot) {
+  CSE_REQUIRE(q && slot >= 0 && slot < q->depth, "pipeline_wait: bad slot");
+  PipeSlot& s = q->slot[slot];
+  if (!s.in_flight) return 0;
+  CSE_CUDA(cudaEventSynchronize(s.d2h));
+  s.in_flight = false;
+  return 0;
+}
+
+int cse_pipeline_destroy(cse_pipeline* q) {
+  pipeline_free(q);
+  return 0;
+}
+
 int cse_masknet_fwd(const cse_params* p, const void* E, const float* ctx, int B, int L, int c,
                     int n_masks, int precision, float* mask, float* pred_head, void* workspace,
                     size_t workspace_bytes, void* stream) {

@@ -369,11 +369,15 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     if (n <= 256 && g_attention_mode != 1 && (n > 64 || g_attention_mode == 2))
       return launch_attention_tc((const bf16*)qkv, nseq, n, (bf16*)out, st);
     const int n_pad = (n + 15) / 16 * 16;
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(attention_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(attention_bf16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      configured = true;
+    static DeviceOnce once;
+    if (!once.configured_on_this_device()) {
+      cudaError_t e1 = cudaFuncSetAttribute(attention_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e8 = cudaFuncSetAttribute(attention_bf16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e1 != cudaSuccess || e8 != cudaSuccess) {
+        set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e8));
+        return 1;
+      }
+      once.mark_configured();
     }
     if (n <= 64) {  // all 8 heads of a sequence in one CTA, one warp per head
       const size_t smem = (size_t)8 * 3 * n_pad * 32 * sizeof(bf16);
@@ -389,10 +393,14 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     return check_launch("attention_bf16_kernel<1>");
   }
   const size_t smem = (size_t)n * kDh * sizeof(float) * 2;
-  static bool configured32 = false;
-  if (!configured32) {
-    cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured32 = true;
+  static DeviceOnce once32;
+  if (!once32.configured_on_this_device()) {
+    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    once32.mark_configured();
   }
   if (smem > 200 * 1024) {
     set_error("attention: sequence of %d tokens does not fit shared memory (fp32)", n);

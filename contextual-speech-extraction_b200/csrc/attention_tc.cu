@@ -344,7 +344,15 @@ typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
 static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
   static AtEncodeFn fn = nullptr;
   static std::mutex mu;
-  static std::unordered_map<uint64_t, CUtensorMap> cache;
+  struct Key {
+    const void* ptr;
+    uint64_t rows;
+    bool operator==(const Key& o) const { return ptr == o.ptr && rows == o.rows; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const { return std::hash<const void*>()(k.ptr) ^ (std::hash<uint64_t>()(k.rows) * 1000003ull); }
+  };
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
   std::lock_guard<std::mutex> g(mu);
   if (fn == nullptr) {
     void* p = nullptr;
@@ -356,7 +364,7 @@ static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
     }
     fn = reinterpret_cast<AtEncodeFn>(p);
   }
-  const uint64_t key = (uint64_t)(uintptr_t)qkv * 1000003ull + rows;
+  const Key key{qkv, rows};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -383,21 +391,17 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     set_error("attention_tc: n=%d outside [1,256]", n);
     return 1;
   }
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static DeviceOnce once;
+  if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAtSmem);
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return 1;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    configured = true;
+    once.mark_configured();
   }
+  const int sms = sm_count();
   CUtensorMap tm;
   if (at_tensor_map(qkv, (uint64_t)nseq * n, &tm)) return 1;
   const int g = n <= 128 ? 128 / n : 0;

@@ -454,10 +454,14 @@ int launch_attention_bwd(const float* qkv, const float* out, const float* d_out,
     set_error("attention_bwd: sequence of %d tokens does not fit shared memory (limit 390)", n);
     return 1;
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
+  static DeviceOnce once;
+  if (!once.configured_on_this_device()) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    once.mark_configured();
   }
   int threads = (n + 31) / 32 * 32;
   if (threads > kAttnBwdThreads) threads = kAttnBwdThreads;

@@ -162,6 +162,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---- per-device one-time setup ----
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per device: a process that touches a second
+// GPU (cuda:1 after cuda:0) must repeat the opt-in there.  `configured_on_this_device()` returns true once the caller
+// has called `mark_configured()` on the CURRENT device.
+struct DeviceOnce {
+  unsigned long long done = 0;  // one bit per device ordinal (ordinals >= 64 are simply re-configured every call)
+  bool configured_on_this_device() const {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < 64 && ((done >> dev) & 1ull);
+  }
+  void mark_configured() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) done |= 1ull << dev;
+  }
+};
+int sm_count();  // gemm_tc.cu: multiprocessors of the CURRENT device
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

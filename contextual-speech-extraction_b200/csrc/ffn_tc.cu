@@ -364,14 +364,14 @@ int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2
     set_error("ffn_tc: operands must be 16-byte aligned");
     return 1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfnSmem);
     if (e != cudaSuccess) {
       set_error("ffn_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", kFfnSmem, cudaGetErrorString(e));
       return 1;
     }
-    configured = true;
+    once.mark_configured();
   }
   CUtensorMap tmA, tmW1, tmW2, tmR;
   if (get_tensor_map(A, (uint64_t)M, kD, kD, 128, 64, 2, &tmA)) return 1;

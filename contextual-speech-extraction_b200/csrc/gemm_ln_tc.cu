@@ -285,15 +285,15 @@ int launch_gemm_ln_tc(const float* R, const float* gamma, const float* beta, flo
     set_error("gemm_ln_tc: operands must be 16-byte aligned");
     return 1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kLnSmem);
     if (e != cudaSuccess) {
       set_error("gemm_ln_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", kLnSmem, cudaGetErrorString(e));
       return 1;
     }
-    configured = true;
+    once.mark_configured();
   }
   CUtensorMap tmW, tmC;
   if (get_tensor_map(W, (uint64_t)N, (uint64_t)kN, (uint64_t)kN, 128, 64, 2, &tmW)) return 1;  // half tile per CTA

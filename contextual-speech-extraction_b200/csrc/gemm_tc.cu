@@ -53,203 +53,13 @@ constexpr int kUmmaK = 16;
 #endif
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers
+// PTX wrappers: tc_ptx.cuh (shared with ffn_tc.cu / attention_tc.cu / gemm_ln_tc.cu); only what is
+// specific to this kernel is defined here.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware
-      : "memory");                               // instead of burning issue slots while it polls
-  return ok != 0;
-}
-// Latency-critical single-thread roles (TMA producer, MMA issuer) poll WITHOUT the suspend hint:
-// a sleeping thread wakes late and every handoff in the load -> MMA -> release ring pays for it.
-__device__ __forceinline__ bool mbar_try_wait_spin(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait_spin(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_spin(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("gemm_tc: mbarrier timeout (tag %d, block %d, thread %d, parity %u)\n", tag,
-             (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-// Bounded wait (~2 s at 2 GHz): a broken pipeline traps with a message instead of hanging.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("gemm_tc: mbarrier timeout (tag %d, block %d, thread %d, parity %u)\n", tag,
-             (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// Multicast load: the box lands at the same shared-memory offset in every CTA of `mask` and
-// completes `bytes` on the mbarrier at the same offset in each of them.
-__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
-                                                  int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5}], [%2], %3;\n" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-      "h"(mask)
-      : "memory");
-}
-// ---- CTA-pair mode (cta_group::2): one UMMA spans the two SMs of a cluster ----
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion bytes are counted on an mbarrier that may live in the PEER CTA of the pair
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster,
-                                                 int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                               uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-      "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
-               "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
-                   reinterpret_cast<uint64_t>(tm)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
-                   reinterpret_cast<uint64_t>(tm)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
-               "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
+using namespace tc;
+
+__device__ __forceinline__ void tc_fence_before() { fence_before(); }
+__device__ __forceinline__ void tc_fence_after() { fence_after(); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -263,23 +73,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 }
 
-// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
-// bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1)
-// | [32,46) SBO>>4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2.
+// K-major SWIZZLE_128B operand: 1024 B between 8-row groups (tc::make_desc)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+  return make_desc(smem_addr, 1024, kLayoutSw128);
 }
-// Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32 (cute::UMMA::InstrDescriptor):
-// c_format=1 @4, a_format=1 @7, b_format=1 @10, a_major=0 @15, b_major=0 @16, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+// kind::f16, A/B = bf16 K-major, D = fp32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return tc::make_idesc_bf16(M, N, 0, 0); }
 
 // ------------------------------------------------------------------------------------------
 // kernel
@@ -518,12 +317,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         uint4* stg = reinterpret_cast<uint4*>(stg0_ptr + buf * Cfg::kEpiBufBytes);
         float v[CW];
-        if constexpr (CW == 64) tc::tmem_ld64(t_row + col_local, v);
+        if constexpr (CW == 64) tmem_ld64(t_row + col_local, v);
         else if constexpr (CW == 32) tmem_ld32(t_row + col_local, v);
         else tmem_ld16(t_row + col_local, v);
         if (bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < CW; i += 2) tc::axpy_f32x2(v[i], v[i + 1], bv[i], bv[i + 1], bias_scale);  // FFMA2
+          for (int i = 0; i < CW; i += 2) axpy_f32x2(v[i], v[i + 1], bv[i], bv[i + 1], bias_scale);  // FFMA2
           // prefetch the bias of the chunk this warp handles next (this tile's next chunk, or the first
           // chunk of its next tile): the load latency hides behind the pack/store and the next wait
           const int npt = pt + t_step;
@@ -546,15 +345,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             u.z = __float_as_uint(v[4 * i + 2]);
             u.w = __float_as_uint(v[4 * i + 3]);
           } else if (relu) {
-            u.x = tc::cvt_bf16x2_relu(v[8 * i], v[8 * i + 1]);
-            u.y = tc::cvt_bf16x2_relu(v[8 * i + 2], v[8 * i + 3]);
-            u.z = tc::cvt_bf16x2_relu(v[8 * i + 4], v[8 * i + 5]);
-            u.w = tc::cvt_bf16x2_relu(v[8 * i + 6], v[8 * i + 7]);
+            u.x = cvt_bf16x2_relu(v[8 * i], v[8 * i + 1]);
+            u.y = cvt_bf16x2_relu(v[8 * i + 2], v[8 * i + 3]);
+            u.z = cvt_bf16x2_relu(v[8 * i + 4], v[8 * i + 5]);
+            u.w = cvt_bf16x2_relu(v[8 * i + 6], v[8 * i + 7]);
           } else {
-            u.x = tc::cvt_bf16x2(v[8 * i], v[8 * i + 1]);
-            u.y = tc::cvt_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = tc::cvt_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = tc::cvt_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            u.x = cvt_bf16x2(v[8 * i], v[8 * i + 1]);
+            u.y = cvt_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = cvt_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = cvt_bf16x2(v[8 * i + 6], v[8 * i + 7]);
           }
           stg[lane * kSlots + (i ^ sw)] = u;
         }
@@ -679,14 +478,15 @@ int get_tensor_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, u
   return 0;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+int sm_count() {  // of the CURRENT device (cached per ordinal)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 
@@ -695,15 +495,15 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
                           int N, int K, int relu, cudaStream_t st) {
   using Cfg = TcCfg<BN, PAIR, ARES>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
       return 1;
     }
-    configured = true;
+    once.mark_configured();
   }
   const int pair_tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN);
   const int max_pairs = sm_count() / 2;
@@ -743,7 +543,7 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
                      out_fp32 ? 4 : 2, &tmC))
     return 1;
   const int acc = residual != nullptr ? 1 : 0;
-  static const bool pair_mma = []() {  // CSE_GEMM_PAIR=0 selects the per-CTA UMMA + multicast variant (A/B aid)
+  static const bool pair_mma = []() {  // CSE_GEMM_PAIR=1 selects the cta_group::2 pair-UMMA variant (measured slower: A/B aid)
     const char* e = getenv("CSE_GEMM_PAIR");
     return e != nullptr && e[0] == '1';
   }();

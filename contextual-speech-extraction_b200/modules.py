@@ -320,6 +320,8 @@ class Dual_Computation_Block_CSE(nn.Module):
         self.inter_context_mapper = None
 
     def add_ctx(self):
+        if self.llm_dim != _lib.CTX:
+            _unsupported(f"ctx_dim={self.llm_dim} (the context-mapper kernel is specialised to {_lib.CTX})")
         self.intra_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
         self.inter_context_mapper = nn.Linear(self.llm_dim, self.out_channels)
 
@@ -500,9 +502,12 @@ class _SepformerBase(nn.Module):
     precision = None        # None: follow torch.autocast; or 'fp32' / 'bf16'
     use_cuda_graph = False  # replay each call shape as one CUDA graph (inference)
 
+    max_cached_graphs = 4   # LRU bound on captured call shapes (each holds a full workspace)
+
     def _init_common(self):
         self._table = ParamTable()
         self._graphs = {}
+        self._graph_gen = -1
 
     def _tensors(self):
         out = {}
@@ -520,24 +525,28 @@ class _SepformerBase(nn.Module):
             raise RuntimeError(f"mix must be [B,T], got {tuple(mix.shape)}")
         _check_cuda(mix, "mix")
         prec = resolve_precision(self.precision)
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
-                                        or (ctx is not None and ctx.requires_grad)):
-            if prec == FP32:
-                # training step (train_ContSep.py:384-419, train_ContExt.py:366-389): the same stages as
-                # autograd nodes whose forward AND backward are C-ABI calls (training.py)
-                from . import training
-                return training.forward_train(self._tensors(), mix, ctx, n_masks, want_pred_head)
-            _warn_no_grad(self)
-        dev = mix.device
-        stream = current_stream(dev)
-        mix = mix.contiguous().float()
         B, T = mix.shape
         c = 0
         if ctx is not None:
-            if ctx.dim() != 3 or ctx.size(0) != B or ctx.size(2) != self.masknet.dual_mdl[0].llm_dim:
-                raise RuntimeError(f"ctx must be [B,c,{self.masknet.dual_mdl[0].llm_dim}], got {tuple(ctx.shape)}")
-            ctx = ctx.contiguous().float()
+            llm_dim = self.masknet.dual_mdl[0].llm_dim
+            if ctx.dim() != 3 or ctx.size(0) != B or ctx.size(2) != llm_dim:
+                raise RuntimeError(f"ctx must be [B,c,{llm_dim}], got {tuple(ctx.shape)}")
+            _check_cuda(ctx, "ctx")
             c = ctx.size(1)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (ctx is not None and ctx.requires_grad)):
+            # training step (train_ContSep.py:384-419, train_ContExt.py:366-389): the same stages as autograd
+            # nodes whose forward AND backward are C-ABI calls (training.py).  Under torch.autocast (the
+            # reference's --fp16 / --bf16 switch, train_ContSep.py:383) the transformer layers run their bf16
+            # tensor-core forward / backward; every other stage, the residual stream and the gradients stay fp32
+            # — outputs ALWAYS carry the autograd graph (never a silent graph-less result).
+            from . import training
+            return training.forward_train(self._tensors(), mix, ctx, n_masks, want_pred_head, bf16=(prec == BF16))
+        dev = mix.device
+        stream = current_stream(dev)
+        mix = mix.contiguous().float()
+        if ctx is not None:
+            ctx = ctx.contiguous().float()
         params = self._table.build(self._tensors(), n_masks, prec, stream)
         lib = _lib.load()
         nbytes = lib.cse_workspace_bytes(B, T, c, n_masks, prec)
@@ -559,9 +568,16 @@ class _SepformerBase(nn.Module):
         the bf16 pack is refreshed outside the graph whenever a parameter version changes."""
         B, T, c, n_masks, prec, want_pred = shape_key
         dev = mix.device
-        key = shape_key + (dev, id(params))
-        ent = self._graphs.get(key)
+        if self._graph_gen != self._table.generation:      # parameters re-allocated: every baked-in pointer is stale
+            self._graphs.clear()
+            self._graph_gen = self._table.generation
+        key = shape_key + (dev,)
+        ent = self._graphs.pop(key, None)
+        if ent is not None:
+            self._graphs[key] = ent                          # re-insert: most recently used last
         if ent is None:
+            while len(self._graphs) >= self.max_cached_graphs:   # each entry holds a workspace + I/O buffers
+                self._graphs.pop(next(iter(self._graphs)))
             st = {
                 "mix": torch.empty_like(mix),
                 "ctx": None if ctx is None else torch.empty_like(ctx),
@@ -616,8 +632,81 @@ class _SepformerBase(nn.Module):
                   prec, _lib.ptr(est_host), _lib.ptr(pred_host), C.c_void_p(ws_ptr), ws_len, C.c_void_p(stream))
         return est_host, pred_host
 
+    def host_pipeline(self, B, T, c=0, depth=2, n_masks=None):
+        """Pipelined end-to-end entry (cse_pipeline_*): `depth` forwards in flight, H2D of step i+1 and D2H of
+        step i-1 overlapping the forward of step i, each forward replayed as one CUDA graph."""
+        return HostPipeline(self, B, T, c, n_masks or self._n_masks(), depth)
+
     def _n_masks(self):
         return self.num_spks
 
     def _wants_pred(self):
         return False
+
+
+class HostPipeline:
+    """`submit(mix_host, ctx_host)` -> ticket; `wait(ticket)` -> (est_host [B,T,n_masks], pred_head_host | None).
+    Host tensors must be pinned; the serving-loop shape of test.py:231-245 with the copies off the critical path."""
+
+    def __init__(self, model, B, T, c, n_masks, depth=2):
+        self.model, self.shape, self.depth = model, (B, T, c, n_masks), depth
+        prec = resolve_precision(model.precision)
+        dev = next(model.parameters()).device
+        self._params = model._table.build(model._tensors(), n_masks, prec, current_stream(dev))
+        torch.cuda.synchronize(dev)                                   # the bf16 pack is complete before capture
+        lib = _lib.load()
+        nbytes = lib.cse_pipeline_workspace_bytes(B, T, c, n_masks, prec, depth)
+        if nbytes == 0:
+            raise _lib.CseError(lib.cse_last_error().decode() or "cse_pipeline_workspace_bytes: bad arguments")
+        self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-self._ws.data_ptr()) % 256
+        self._handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.call("cse_pipeline_create", C.byref(self._params), B, T, c, n_masks, prec, depth,
+                      C.c_void_p(self._ws.data_ptr() + off), self._ws.numel() - off, C.byref(self._handle))
+        self._wants_pred = model._wants_pred() and c > 0
+        self._est = [torch.empty(B, T, n_masks, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._pred = [torch.empty(B, N_CH, dtype=torch.float32).pin_memory() if self._wants_pred else None
+                      for _ in range(depth)]
+
+    @staticmethod
+    def _check_host(t, name, shape):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise _lib.CseError(f"{name} must be a contiguous float32 HOST tensor of shape {shape}, got "
+                                f"{tuple(t.shape)} {t.dtype} on {t.device}")
+        if not t.is_pinned():
+            raise _lib.CseError(f"{name} must be pinned (page-locked) host memory for the asynchronous copies")
+
+    def submit(self, mix_host, ctx_host=None, est_host=None):
+        if self._handle is None:
+            raise _lib.CseError("pipeline is closed")
+        B, T, c, n_masks = self.shape
+        self._check_host(mix_host, "mix_host", (B, T))
+        if c:
+            self._check_host(ctx_host, "ctx_host", (B, c, _lib.CTX))
+        slot = C.c_int(-1)
+        # the slot that will be used is the C side's round-robin cursor; its default output buffers are ours
+        nxt = getattr(self, "_next", 0)
+        est = est_host if est_host is not None else self._est[nxt]
+        if est_host is not None:
+            self._check_host(est_host, "est_host", (B, T, n_masks))
+        pred = self._pred[nxt]
+        _lib.call("cse_pipeline_submit", self._handle, _lib.ptr(mix_host), _lib.ptr(ctx_host) if c else None,
+                  _lib.ptr(est), _lib.ptr(pred), C.byref(slot))
+        self._next = (slot.value + 1) % self.depth
+        return (slot.value, est, pred, mix_host, ctx_host)            # keeps the host buffers alive
+
+    def wait(self, ticket):
+        _lib.call("cse_pipeline_wait", self._handle, ticket[0])
+        return ticket[1], ticket[2]
+
+    def close(self):
+        if self._handle is not None:
+            _lib.call("cse_pipeline_destroy", self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -41,6 +41,7 @@ class ParamTable:
         self._pack = None
         self._pack_key = None
         self._keep = None
+        self.generation = 0      # bumped whenever the pointer table is rebuilt (CUDA-graph caches key on it)
 
     @staticmethod
     def _stack(sp, prefix, sd):
@@ -96,7 +97,13 @@ class ParamTable:
             p.gate_b = _dev_f32(sd["masknet.output_gate.0.bias"], "masknet.output_gate.0.bias")
             p.end_w = _dev_f32(sd["masknet.end_conv1x1.weight"], "masknet.end_conv1x1.weight")
             p.dec_w = _dev_f32(sd["decoder.weight"], "decoder.weight")
+            for d in (f"masknet.dual_mdl.{i}." for i in range(BLOCKS)):
+                for k in ("intra_context_mapper.weight", "inter_context_mapper.weight"):
+                    w = sd.get(d + k)
+                    if w is not None and tuple(w.shape) != (_lib.N, _lib.CTX):
+                        raise _lib.CseError(f"{d + k} has shape {tuple(w.shape)}, the kernels need ({_lib.N}, {_lib.CTX})")
             self._params, self._key = p, key
+            self.generation += 1
             self._pack_key = None
             self._keep = list(tensors.values())     # keep storages alive while pointers are cached
         if precision == BF16:

@@ -322,22 +322,25 @@ class MaskDecodeFn(Function):
 # ----------------------------------------------------------------------------------------------
 # composition
 # ----------------------------------------------------------------------------------------------
-def _stack(sd, prefix, X, tok, B, S, c, inter):
+def _stack(sd, prefix, X, tok, B, S, c, inter, bf16=False):
     """SBTransformerBlock_CSE on the chunk tensor: returns (chunks [B,S,K,256], prompt-row sums)."""
     R = BuildSequencesFn.apply(X, tok, sd[prefix + "pos_enc.pe"], inter)
     nseq, n = (B * K, S + c) if inter else (B * S, K + c)
     for l in range(LAYERS):
         q = f"{prefix}mdl.layers.{l}."
-        R = transformer_layer({key: sd[q + key] for _, key in LAYER_KEYS}, R, nseq, n)
+        R = transformer_layer({key: sd[q + key] for _, key in LAYER_KEYS}, R, nseq, n, bf16)
     R = LayerNormFn.apply(R, sd[prefix + "mdl.norm.norm.weight"], sd[prefix + "mdl.norm.norm.bias"])
     return SequencesToChunksFn.apply(R, B, S, c, inter)
 
 
-def forward_train(sd, mix, ctx, n_masks, want_pred_head=False):
+def forward_train(sd, mix, ctx, n_masks, want_pred_head=False, bf16=False):
     """Differentiable encoder -> masknet(ctx) -> mask * mix_w -> decoder -> pad/trim.
 
     sd: {reference state_dict key -> tensor} (`_SepformerBase._tensors()`); mix [B,T]; ctx [B,c,4096] or
-    None.  Returns (est [B,T,n_masks], pred_head [B,256] | None), same as `_SepformerBase._run`."""
+    None.  Returns (est [B,T,n_masks], pred_head [B,256] | None), same as `_SepformerBase._run`.
+    bf16 (the step runs under torch.autocast): the 32 transformer layers — 97 % of the FLOPs — use the bf16
+    tensor-core kernels forward and backward; every other stage, the residual stream, the norms, the losses and all
+    gradients stay fp32 (autocast keeps them fp32 too)."""
     mix = _f32(mix, "mix")
     B, T = mix.shape
     c = 0
@@ -360,10 +363,10 @@ def forward_train(sd, mix, ctx, n_masks, want_pred_head=False):
                                        sd[p + "intra_context_mapper.bias"]).view(B, c, N)
             tok_e = ContextMapFn.apply(flat, sd[p + "inter_context_mapper.weight"],
                                        sd[p + "inter_context_mapper.bias"]).view(B, c, N)
-        Y, _ = _stack(sd, p + "intra_mdl.", X, tok_i, B, S, c, False)
+        Y, _ = _stack(sd, p + "intra_mdl.", X, tok_i, B, S, c, False, bf16)
         X1 = GroupNormFn.apply(Y.view(B, S * K, N), sd[p + "intra_norm.weight"], sd[p + "intra_norm.bias"],
                                X.view(B, S * K, N)).view(B, S, K, N)
-        Y, tok_sum = _stack(sd, p + "inter_mdl.", X1, tok_e, B, S, c, True)
+        Y, tok_sum = _stack(sd, p + "inter_mdl.", X1, tok_e, B, S, c, True, bf16)
         if want_pred_head and c:
             pred_head = tok_sum[:, 0, :] / K                               # ContSep.py:516-517
         X = GroupNormFn.apply(Y.view(B, S * K, N), sd[p + "inter_norm.weight"], sd[p + "inter_norm.bias"],

@@ -160,6 +160,23 @@ CSE_API int cse_forward_host(const cse_params* p_host, const float* mix_host, co
                              float* est_host, float* pred_head_host,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pipelined host entry: `depth` forwards in flight (serving / eval loops, test.py:231-245 per batch).
+ * Each slot owns one cse_workspace_bytes() region of the caller's workspace (device staging of its inputs and
+ * outputs included) and a CUDA graph of the forward captured at create time; H2D, forward and D2H run on three
+ * internal streams chained by events, so the copy-in of step i+1 and the copy-out of step i-1 overlap the forward
+ * of step i.  The graph bakes in the pointers of `p_host` (bf16 pack included): keep them alive and unchanged, and
+ * re-create the pipeline after a parameter re-allocation.  Host buffers must be pinned and stay valid until the
+ * slot is waited on.  submit() on a slot that is still in flight waits for it first.
+ *   cse_pipeline_submit  -> *slot: pass it to cse_pipeline_wait to collect est_host / pred_head_host. */
+typedef struct cse_pipeline cse_pipeline;
+CSE_API size_t cse_pipeline_workspace_bytes(int B, int T, int c, int n_masks, int precision, int depth);
+CSE_API int cse_pipeline_create(const cse_params* p_host, int B, int T, int c, int n_masks, int precision,
+                                int depth, void* workspace, size_t workspace_bytes, cse_pipeline** out);
+CSE_API int cse_pipeline_submit(cse_pipeline* pipe, const float* mix_host, const float* ctx_host,
+                                float* est_host, float* pred_head_host, int* slot);
+CSE_API int cse_pipeline_wait(cse_pipeline* pipe, int slot);
+CSE_API int cse_pipeline_destroy(cse_pipeline* pipe);
+
 /* Dual_Path_Model_CSE.forward on its own (ContSep.py:205-268; speechbrain Dual_Path_Model when
  * c == 0): E = mix_w channels-last [B,L,256] in the activation dtype of `precision` ->
  * mask [B,L,n_masks,256] fp32 (post-ReLU; reference layout mask[s,b,n,l]) and pred_head. */
