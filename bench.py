@@ -8,11 +8,17 @@ step   : one forward of the ContSep 2-spk model over one batch (configs[1]: 16 m
          synthetic 4096-d context embeddings, bf16 tensor-core mode) per GPU; weak scaling —
          every rank separates its own batch, no data-path collective (mixtures are independent).
 value  : whole-job audio-s / max-over-ranks device time, inputs already resident in HBM.
-e2e    : same metric through the host-buffer C-ABI entry (cse_forward_host): pinned host mixtures
-         -> H2D -> forward -> D2H of the separated waveforms, every step.
+e2e    : same metric through the host-buffer C-ABI entry: pinned host mixtures -> H2D -> forward -> D2H of
+         the separated waveforms, every step; `value` = the pipelined entry (cse_pipeline_*, two steps in
+         flight), `blocking_call_value` = one blocking cse_forward_host call per step.
+parity : mixtures 0 and 15 of the timed batch checked against the CPU oracle outside the timed region.
+train  : BASELINE configs[2] measured in the same process (ContExt forward + -SI-SNR + backward + DDP gradient
+         all-reduce + clip + AdamW under autocast, 2 mixtures x 4 s per GPU) so that the driver's 1 -> 8 GPU runs
+         time the one collective this path has.
 roofline / cpu_baseline: see DESIGN.md §Measurement.
---impl reference: the oracle port of the reference's CPU path (the Python reference itself cannot
-travel to the GPU box), all host threads, one 4 s mixture per step.
+--impl reference: the reference's CPU path — its op sequence on the stock torch modules it instantiates
+(oracle/eager_reference.py; the Python reference itself cannot travel to the GPU box), all host threads, one 4 s
+mixture per step.
 --workload train (not the driver's default): BASELINE configs[2] — ContExt forward + -SI-SNR loss +
 backward + gradient all-reduce (stock DDP over NCCL) + clip + AdamW, 2 mixtures x 4 s per GPU, fp32
 parity-mode kernels (the bf16 tensor-core backward is not built yet).
@@ -97,21 +103,28 @@ class ClockSampler:
 
 
 def cpu_reference_rate(steps, warmup):
-    """Oracle port of the reference's CPU path: one 4 s mixture per step, fp32, all host threads."""
+    """The reference's own CPU path: its op sequence on the stock torch modules it instantiates (nn.MultiheadAttention,
+    nn.LayerNorm, nn.GroupNorm, nn.Conv1d, ... — `oracle/eager_reference.py`, bit-identical to the reference modules'
+    fp32 output, tests/test_oracle.py), one 4 s mixture per step, fp32, all host threads.  The parameters sit in our
+    module mirror used as a plain container on the CPU; no kernel of ours runs."""
     import torch
     import cse_b200  # noqa: F401
     from cse_b200 import synth
-    from oracle import sepformer_oracle as O
+    from cse_b200.models.ContSep import Sepformer
+    from oracle import eager_reference as ER
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synth.make_state_dict("contsep", SPK, seed=0)
+    model = Sepformer(SPK, add_mt=True)
+    model.add_mt_pipeline()
+    model.load_state_dict(synth.make_state_dict("contsep", SPK, seed=0))
+    model.eval()
     mix, _ = synth.make_mixture(1, T, SPK, seed=1234)
     ctx = synth.make_context(1, CTX_TOKENS, seed=1234)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.sepformer_forward(sd, mix, ctx, "contsep", SPK)
+            ER.eager_forward(model, mix, ctx)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
@@ -140,7 +153,7 @@ def run_reference(args):
         }), flush=True)
         return
     value, per_step, cores = cpu_reference_rate(steps, warmup)
-    sample = f"1 mixture x {SECONDS} s per step ({steps} timed steps, {warmup} warm-up), fp32, oracle port of the reference modules"
+    sample = f"1 mixture x {SECONDS} s per step ({steps} timed steps, {warmup} warm-up), fp32, the reference's op sequence on its own stock torch modules (oracle/eager_reference.py, bit-identical to the reference output)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
@@ -151,6 +164,65 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def _op_point_dsisnr(est, gold):
+    """max |SI-SNR(est, target) - SI-SNR(gold, target)| in dB over streams, targets = gold + seeded noise such that
+    SI-SNR(gold, target) = 0 / 10 / 15 dB (the range the metric is used at)."""
+    import torch
+    from oracle import sepformer_oracle as O
+    g = torch.Generator().manual_seed(99)
+    noise = torch.randn(gold.shape, generator=g, dtype=torch.float64)
+    gz = gold.double() - gold.double().mean(1, keepdim=True)
+    worst = 0.0
+    for level_db in (0.0, 10.0, 15.0):
+        scale = (gz.pow(2).sum(1, keepdim=True) / noise.pow(2).sum(1, keepdim=True)).sqrt() * 10 ** (-level_db / 20)
+        target = gold.double() + noise * scale
+        for s in range(gold.shape[2]):
+            a = O.tm_si_snr(est[:, :, s].double(), target[:, :, s])
+            b = O.tm_si_snr(gold[:, :, s].double(), target[:, :, s])
+            worst = max(worst, (a - b).abs().max().item())
+    return worst
+
+
+def parity_check(model, sd, mix_h, ctx_h, est_bf16, pred_bf16, dev):
+    """Outside the timed region: mixtures 0 and 15 of the timed batch against the CPU oracle (fp32), for the bf16
+    output that was just timed and for one fp32-mode forward of the same two mixtures."""
+    import numpy as np
+    import torch
+    from oracle import sepformer_oracle as O
+    idx = [0, BATCH - 1]
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = [O.sepformer_forward(sd, mix_h[i:i + 1], ctx_h[i:i + 1], "contsep", SPK) for i in idx]
+    ref_est = torch.cat([r[0] for r in ref], 0)
+    ref_pred = torch.cat([r[1] for r in ref], 0)
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    model.precision, graph = "fp32", model.use_cuda_graph
+    model.use_cuda_graph = False
+    with torch.no_grad():
+        est32, pred32 = model(mix_h[idx].to(dev), ctx_h[idx].to(dev))
+    model.precision, model.use_cuda_graph = "bf16", graph
+    e16, p16 = est_bf16[idx].cpu(), pred_bf16[idx].cpu()
+    out = {"checked_mixtures": idx, "against": "CPU oracle (fp32), live",
+           "fp32_rel_l2": rel(est32.cpu(), ref_est), "fp32_context_pred_rel_l2": rel(pred32.cpu(), ref_pred),
+           "bf16_rel_l2": rel(e16, ref_est), "bf16_context_pred_rel_l2": rel(p16, ref_pred),
+           "bf16_dsisnr_db": _op_point_dsisnr(e16, ref_est),
+           "tolerance": "fp32 <= 1e-4 rel-L2; bf16 <= 0.05 dB SI-SNR at 0/10/15 dB operating points and rel-L2 <= the reference's own bf16 drift"}
+    drift = []
+    for i in idx:
+        f = os.path.join(ROOT, "tests", "golden", f"baseline_cfg2_mix{i}.npz")
+        if os.path.isfile(f):
+            with np.load(f) as z:
+                drift.append(float(z["bf16_ref_rel_l2"]))
+    if drift:
+        out["reference_bf16_rel_l2"] = max(drift)
+    out["ok"] = bool(out["fp32_rel_l2"] <= 1e-4 and out["bf16_dsisnr_db"] <= 0.05
+                     and (not drift or out["bf16_rel_l2"] <= max(drift)))
+    return out
 
 
 def gemm_flops_per_forward(ps):
@@ -241,12 +313,22 @@ def run_ours(args):
     def step_host():
         model.separate_host(mix_h, ctx_h, est_host=est_h)
 
+    pipe = model.host_pipeline(BATCH, T, c=CTX_TOKENS, depth=2)
+    in_flight = []
+
+    def step_pipelined():      # submit step i (H2D + forward + D2H enqueued), then collect step i-1
+        in_flight.append(pipe.submit(mix_h, ctx_h))
+        if len(in_flight) > 1:
+            pipe.wait(in_flight.pop(0))
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     step_host()
+    for _ in range(3):
+        step_pipelined()
     torch.cuda.synchronize()
     if rank == 0:
         sampler.lines.clear()          # keep only samples taken during the timed regions
@@ -265,7 +347,12 @@ def run_ours(args):
     # end to end through the host-buffer entry: device time is not enough here (the call blocks on
     # the D2H), so use the max-over-ranks wall clock around the loop
     _, wall = timed(step_host, args.steps)
+    e2e_blocking = audio_s / (wall / args.steps)
+    # pipelined: K submits, K results; the loop's trailing in-flight step completes inside timed()'s synchronize
+    _, wall = timed(step_pipelined, args.steps)
     e2e_value = audio_s / (wall / args.steps)
+    while in_flight:
+        pipe.wait(in_flight.pop(0))
     clocks = sampler.stop() if rank == 0 else None
     h2d = BATCH * T * 4 + BATCH * CTX_TOKENS * 4096 * 4
     d2h = BATCH * T * SPK * 4 + BATCH * 256 * 4
@@ -307,11 +394,23 @@ def run_ours(args):
                            "unit": "TFLOP/s", "frac": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]},
         }
 
+    parity = None
+    if rank == 0:
+        est_bf16, pred_bf16 = step_device()
+        torch.cuda.synchronize()
+        parity = parity_check(model, sd, mix_h, ctx_h, est_bf16, pred_bf16, dev)
+    pipe.close()
+    del pipe
+
+    train = None
+    if not args.no_train:
+        train = measure_train(args, world, rank, local, dev, steps=max(3, min(args.steps, 10)), quiet=True)
+
     cpu = None
     if rank == 0 and world == 1:
         v, per_step, cores = cpu_reference_rate(3, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 of the 16 mixtures ({SECONDS} s) per forward, 3 timed forwards + 1 warm-up, fp32 oracle port, {cores} threads"}
+               "sample": f"1 of the 16 mixtures ({SECONDS} s) per forward, 3 timed forwards + 1 warm-up, fp32, the reference's op sequence on stock torch modules, {cores} threads"}
 
     if rank == 0:
         print(json.dumps({
@@ -323,8 +422,10 @@ def run_ours(args):
                        "num_spks": SPK, "weights": "random-init (seeded)", "sharding": f"dp{world}: independent mixtures, no collective",
                        "l2": "no flush: one step streams ~1.4 GB of activations through a 126 MB L2"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "api": "Sepformer.separate_host -> cse_forward_host (pinned host buffers)"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                                      "api": "Sepformer.host_pipeline -> cse_pipeline_submit / cse_pipeline_wait (pinned host buffers, 2 steps in flight, every step's H2D and D2H inside the timed region)",
+                                      "blocking_call_value": e2e_blocking,
+                                      "blocking_call_api": "Sepformer.separate_host -> cse_forward_host (one blocking call per step)"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "train": train,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -363,8 +464,11 @@ def cpu_train_rate(steps, warmup, seconds=SECONDS, loss_kind="sisnr"):
     return seconds / per_step, per_step, cores
 
 
-def run_train(args):
-    """BASELINE configs[2]: ContExt forward+backward, batch 2 per GPU, data-parallel (weak scaling)."""
+def measure_train(args, world, rank, local, dev, steps, quiet=False):
+    """BASELINE configs[2]: ContExt forward + loss + backward + DDP gradient all-reduce + clip + AdamW(amsgrad),
+    batch 2 per GPU (weak scaling), under torch.autocast like the reference (train_ContExt.py:365) unless
+    --train-precision fp32.  Returns the result dict on rank 0 (None elsewhere).  The process group must exist when
+    world > 1."""
     import torch
     import torch.distributed as dist
     import cse_b200  # noqa: F401
@@ -373,19 +477,9 @@ def run_train(args):
     from cse_b200.models.ContSep import Sepformer as ContSep
 
     seconds, loss_kind = args.train_seconds, args.train_loss
+    amp = args.train_precision != "fp32"
     Tt = seconds * SR
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-
     if loss_kind == "pit":       # train_ContSep.py: PIT SI-SNR + cross-entropy on the context selector
         model = ContSep(SPK, add_mt=True)
         model.add_mt_pipeline()
@@ -395,35 +489,56 @@ def run_train(args):
         model.add_ctx_pipeline()
         model.load_state_dict(synth.make_state_dict("context", SPK, seed=0))
     model = model.to(dev).train()
-    model.precision = "fp32"
+    model.precision = None if amp else "fp32"
     net = model
     if world > 1:   # the reference's own wrapper (train_ContExt.py:269-273): bucketed NCCL all-reduce overlapped with backward
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, amsgrad=True)      # train_ContSep.py:233
     sisnr = losses.ScaleInvariantSignalNoiseRatio()
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
 
+    if args.train_ragged:        # DailyTalk-like lengths U(1.5 s, 8 s), right-padded to the batch max (dataset_train_CSE.py:532-569)
+        g = torch.Generator().manual_seed(777 + rank)
+        lens = (torch.rand(TRAIN_BATCH, generator=g) * 6.5 + 1.5) * SR
+        lens = [int(x) // 8 * 8 for x in lens.tolist()]
+        Tt = max(lens)
     mix_h, src_h = synth.make_mixture(TRAIN_BATCH, Tt, SPK, seed=4321 + rank)
+    if args.train_ragged:
+        for i, n in enumerate(lens):
+            mix_h[i, n:] = 0
+            src_h[i, n:] = 0
     ctx_h = synth.make_context(TRAIN_BATCH, CTX_TOKENS, seed=4321 + rank)
     tgt_h = (src_h if loss_kind == "pit" else src_h[:, :, 0]).contiguous().pin_memory()
     label = torch.zeros(TRAIN_BATCH, dtype=torch.long, device=dev)
     mix_h, ctx_h = mix_h.pin_memory(), ctx_h.pin_memory()
     mix_d, ctx_d, tgt_d = mix_h.to(dev), ctx_h.to(dev), tgt_h.to(dev)
 
-    def step(mix, ctx, tgt):
-        opt.zero_grad(set_to_none=True)
-        if loss_kind == "pit":
-            est, pred = net(mix, ctx)
-            loss = (losses.get_si_snr_with_pitwrapper(est, tgt).mean()       # train_ContSep.py:391-394
-                    + torch.nn.functional.cross_entropy(pred, label))
-        else:
-            est = net(mix, ctx)
-            loss = -sisnr(est[:, :, 0], tgt)                                # train_ContExt.py:366-367
+    def fwd_bwd(module, mix, ctx, tgt):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):      # train_ContExt.py:365 (--bf16)
+            if loss_kind == "pit":
+                est, pred = module(mix, ctx)
+                loss = (losses.get_si_snr_with_pitwrapper(est, tgt).mean()   # train_ContSep.py:391-394
+                        + torch.nn.functional.cross_entropy(pred.float(), label))
+            else:
+                est = module(mix, ctx)
+                loss = -sisnr(est[:, :, 0], tgt)                            # train_ContExt.py:366-367
         loss.backward()
+        return loss
+
+    def step(mix, ctx, tgt, module=None):
+        opt.zero_grad(set_to_none=True)
+        loss = fwd_bwd(module or net, mix, ctx, tgt)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)             # train_ContSep.py:411
         opt.step()
         return loss
 
     def step_device():
+        return step(mix_d, ctx_d, tgt_d)
+
+    def step_no_allreduce():     # the same step without the collective (DDP.no_sync): what the all-reduce adds
+        if world > 1:
+            with net.no_sync():
+                return step(mix_d, ctx_d, tgt_d)
         return step(mix_d, ctx_d, tgt_d)
 
     def step_host():
@@ -437,12 +552,12 @@ def run_train(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, k):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         e1.record()
         torch.cuda.synchronize()
@@ -456,56 +571,91 @@ def run_train(args):
         return ms, wall
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not quiet:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
-    if rank == 0:
+    if rank == 0 and not quiet:
         sampler.lines.clear()
     n0 = lib.cse_launch_count()
-    step_device()
+    loss0 = step_device()
     launches = lib.cse_launch_count() - n0
-    ms_total, _ = timed(step_device, args.steps)
-    ms_step = ms_total / args.steps
-    audio_s = TRAIN_BATCH * seconds * world
+    ms_total, _ = timed(step_device, steps)
+    ms_step = ms_total / steps
+    audio_s = TRAIN_BATCH * (Tt / SR) * world
     value = audio_s / (ms_step / 1e3)
-    _, wall = timed(step_host, args.steps)
-    e2e_value = audio_s / (wall / args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    _, wall = timed(step_host, steps)
+    e2e_value = audio_s / (wall / steps)
+    comm = None
+    if world > 1:
+        ms_nosync, _ = timed(step_no_allreduce, steps)
+        flat = torch.zeros(n_params, dtype=torch.float32, device=dev)
 
-    roofline = cpu = None
+        def allreduce_alone():   # the same bytes in DDP's default 25 MB buckets, nothing else running
+            for chunk in flat.split(25 * 1024 * 1024 // 4):
+                dist.all_reduce(chunk)
+
+        ms_ar, _ = timed(allreduce_alone, steps)
+        exposed = max(0.0, ms_step - ms_nosync / steps)
+        alone = ms_ar / steps
+        comm = {"collective": "NCCL all-reduce of fp32 gradients (stock DistributedDataParallel, 25 MB buckets)",
+                "allreduce_bytes_per_step": n_params * 4, "step_ms": ms_step, "step_ms_without_allreduce": ms_nosync / steps,
+                "exposed_allreduce_ms": exposed, "allreduce_alone_ms": alone,
+                "overlap_fraction": max(0.0, min(1.0, 1.0 - exposed / alone)) if alone > 0 else None}
+    clocks = sampler.stop() if (rank == 0 and not quiet) else None
+    if rank != 0:
+        return None
+    ps = shapes.path_shape(TRAIN_BATCH, Tt, CTX_TOKENS, SPK if loss_kind == "pit" else 1)
+    peaks = load_peaks()
+    # forward + recomputed forward (layer checkpointing) + dgrad + wgrad = 4x the forward contractions
+    flops = 4.0 * shapes.algorithmic_flops(ps)
+    achieved = flops / (ms_step * 1e-3) / 1e12
+    kernels = ("cse::gemm_tc_kernel / ffn-free bf16 layers + attention (tcgen05 forward, recompute, dgrad, wgrad)" if amp
+               else "cse::gemm_simt_kernel / wgrad_kernel / attention_f32 + attention_bwd (fp32 FFMA parity mode)")
+    roofline = {"kernel": "whole step: " + kernels, "bound": "tensor", "achieved": achieved,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS)", "traffic": None}
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if amp else "f32", "data": "synthetic",
+        "config": {"workload": ("ContSep 2-spk forward + PIT SI-SNR + selector CE" if loss_kind == "pit" else
+                                "ContExt 2-spk forward + -SI-SNR loss")
+                   + " + backward + grad all-reduce + clip + AdamW (BASELINE.json configs[2])",
+                   "batch_per_gpu": TRAIN_BATCH, "seconds": Tt / SR, "ragged_lengths": bool(args.train_ragged),
+                   "sample_rate": SR, "ctx_tokens": CTX_TOKENS, "num_spks": SPK, "weights": "random-init (seeded)",
+                   "precision": "torch.autocast(bfloat16): bf16 tensor-core transformer layers, fp32 elsewhere" if amp else "fp32",
+                   "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
+                   "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
+        "clocks": clocks, "loss": float(loss0.item()), "n_params": n_params, "comm": comm,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() + ctx_h.numel() + tgt_h.numel()) * 4,
+                "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
+        "gpu_launches": int(launches), "roofline": roofline,
+    }
+
+
+def run_train(args):
+    """--workload train: the configs[2] measurement on its own line."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    res = measure_train(args, world, rank, local, dev, steps=args.steps)
     if rank == 0:
-        ps = shapes.path_shape(TRAIN_BATCH, Tt, CTX_TOKENS, SPK if loss_kind == "pit" else 1)
-        peaks = load_peaks()
-        # forward + recomputed forward (layer checkpointing) + dgrad + wgrad = 4x the forward contractions
-        flops = 4.0 * shapes.algorithmic_flops(ps)
-        achieved = flops / (ms_step * 1e-3) / 1e12
-        roofline = {"kernel": "whole step: cse::gemm_simt_kernel / wgrad_kernel / attention_f32 + attention_bwd (fp32 FFMA parity mode)",
-                    "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops_sustained"], "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS)",
-                    "traffic": None,
-                    "note": "fp32 SIMT kernels: this fraction is against the bf16 tensor peak the tcgen05 backward will be held to"}
         if world == 1:
-            v, per_step, cores = cpu_train_rate(2, 1, seconds, loss_kind)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1 mixture ({seconds} s) forward+backward per step under autograd, 2 timed steps + 1 warm-up, fp32 oracle port, {cores} threads"}
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("ContSep 2-spk forward + PIT SI-SNR + selector CE" if loss_kind == "pit" else
-                                    "ContExt 2-spk forward + -SI-SNR loss")
-                       + " + backward + grad all-reduce + clip + AdamW (BASELINE.json configs[2])",
-                       "batch_per_gpu": TRAIN_BATCH, "seconds": seconds, "sample_rate": SR, "ctx_tokens": CTX_TOKENS,
-                       "num_spks": SPK, "weights": "random-init (seeded)",
-                       "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
-                       "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() + ctx_h.numel() + tgt_h.numel()) * 4,
-                    "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        }), flush=True)
+            v, per_step, cores = cpu_train_rate(2, 1, args.train_seconds, args.train_loss)
+            res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"1 mixture ({args.train_seconds} s) forward+backward per step under autograd, 2 timed steps + 1 warm-up, fp32 oracle port, {cores} threads"}
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -521,6 +671,11 @@ def main():
     ap.add_argument("--train-seconds", type=int, default=SECONDS, help="--workload train: mixture length (4; 16 = max_sp_len cap)")
     ap.add_argument("--train-loss", default="sisnr", choices=["sisnr", "pit"],
                     help="--workload train: ContExt -SI-SNR (train_ContExt.py:367) or ContSep PIT + selector CE (train_ContSep.py:391-394)")
+    ap.add_argument("--train-precision", default="autocast", choices=["autocast", "fp32"],
+                    help="training leg: torch.autocast(bf16) like the reference's --bf16 (tensor-core layers), or the fp32 parity kernels")
+    ap.add_argument("--train-ragged", action="store_true",
+                    help="training leg: DailyTalk-like lengths U(1.5 s, 8 s) right-padded to the batch max instead of fixed --train-seconds")
+    ap.add_argument("--no-train", action="store_true", help="forward workload: skip the `train` sub-object")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

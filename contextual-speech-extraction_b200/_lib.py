@@ -58,6 +58,7 @@ _SIGNATURES = {
     "cse_last_error": (C.c_char_p, []),
     "cse_launch_count": (C.c_longlong, []),
     "cse_debug_force_mma_attention": (C.c_int, [C.c_int]),
+    "cse_debug_attention_trace": (C.c_int, [_v]),
     "cse_profile_enable": (C.c_int, [C.c_int]),
     "cse_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "cse_path_shape": (C.c_int, [C.c_int] * 4 + [C.POINTER(Shape)]),

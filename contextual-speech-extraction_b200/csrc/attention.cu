@@ -366,7 +366,7 @@ int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaS
     // sequences (inter stack beyond ~30 s of audio) use the online-softmax mma.sync kernel below
     // Very short sequences (inter stack at <= 8 s of audio) are latency- not exp-bound and run
     // faster with all 8 heads of a sequence in one mma.sync CTA (measured 122 vs 163 us at n = 35).
-    if (n <= 256 && g_attention_mode != 1 && (n > 64 || g_attention_mode == 2))
+    if (n <= 256 && g_attention_mode != 1 && (n > 64 || g_attention_mode >= 2))
       return launch_attention_tc((const bf16*)qkv, nseq, n, (bf16*)out, st);
     const int n_pad = (n + 15) / 16 * 16;
     static DeviceOnce once;

@@ -19,6 +19,7 @@
 //      lands in the first 32 TMEM columns of the chunk's own, already consumed, score columns
 //   -> the same threads read the O_c, re-weight them by 2^(m_c - m_final) (<= 1), divide by the
 //      re-weighted row sum and store bf16.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -335,6 +336,319 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// v2: same arithmetic, re-plumbed so that the MUFU (softmax) and tensor-pipe (S, PV) phases of the two items in
+// flight overlap instead of adding up (profiles/r01_ncu_full_layer.txt: 260 k cycles per launch = 122 k cycles of
+// MUFU.EX2 + ~140 k cycles of N = 32 / N = 256 UMMAs issued back to back):
+//   * ONE issuing warp polls (mbarrier.test_wait) every pending piece of tensor work of both in-flight items and
+//     issues whichever is ready — S of the next item first.  v1's PV warp walked the items in order, so the four PV
+//     chunks of item k+1 queued behind the last softmax chunk of item k, and S of item k+2 queued behind those.
+//   * P never touches shared memory: the bf16 probabilities go back into the item's own consumed score columns
+//     (tcgen05.st) and feed P_c V_c as the TMEM A operand; O_c lands beside them.  No generic->async proxy fence,
+//     no swizzled STS, and the 128 KB of P staging become a 4-deep Q/K/V ring, so V is resident long before its
+//     first P_c V_c instead of being requested when the previous item on the buffer finishes.
+// TMEM columns of buffer b (256 per item): chunk c (64 keys) = [64c, 64c+64): scores -> P_c in [64c, 64c+32)
+// (two bf16 per column), O_c (fp32 [128 x 32]) in [64c+32, 64c+64).
+// ------------------------------------------------------------------------------------------
+constexpr int kA2Threads = 320;  // warp 0 TMA, warp 1 S/PV issuer, warps 2-5 softmax group 0, warps 6-9 group 1
+constexpr int kA2Stages = 4;
+constexpr int kA2StageBytes = kAtQ + 2 * kAtKV;  // 40 KB: Q tile + K + V
+constexpr size_t kA2Smem = 1024 + (size_t)kA2Stages * kA2StageBytes + 512;
+constexpr int kA2TraceSlots = 16, kA2TraceItems = 64;
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
+                     int g, int items, long long* __restrict__ trace) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t sBar = smem_base + kA2Stages * kA2StageBytes;
+  // per stage: QK_FULL, V_FULL, QK_EMPTY, V_EMPTY; per TMEM buffer: S_FULL, O_FULL, FREE, P[4]
+  auto bar_st = [&](int which, int st) -> uint32_t { return sBar + (uint32_t)(which * kA2Stages + st) * 8; };
+  enum { QK_FULL = 0, V_FULL = 1, QK_EMPTY = 2, V_EMPTY = 3 };
+  const uint32_t sBarB = sBar + 4 * kA2Stages * 8;
+  auto bar_b = [&](int which, int b) -> uint32_t { return sBarB + (uint32_t)(which * 2 + b) * 8; };
+  enum { S_FULL = 0, O_FULL = 1, FREE = 2 };
+  auto bar_p = [&](int b, int cp) -> uint32_t { return sBarB + (uint32_t)(6 + b * 4 + cp) * 8; };
+  const uint32_t tmem_slot = sBarB + 14 * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+  auto sQ = [&](int st) { return smem_base + (uint32_t)st * kA2StageBytes; };
+  auto sK = [&](int st) { return smem_base + (uint32_t)st * kA2StageBytes + kAtQ; };
+  auto sV = [&](int st) { return smem_base + (uint32_t)st * kA2StageBytes + kAtQ + kAtKV; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = blockIdx.x < items ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int k, int slot) {
+    if (tracing && k < kA2TraceItems) trace[k * kA2TraceSlots + slot] = clock64();
+  };
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kA2Stages; ++st) {
+      mbar_init(bar_st(QK_FULL, st), 1);
+      mbar_init(bar_st(V_FULL, st), 1);
+      mbar_init(bar_st(QK_EMPTY, st), 1);
+      mbar_init(bar_st(V_EMPTY, st), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_b(S_FULL, b), 1);
+      mbar_init(bar_b(O_FULL, b), 1);
+      mbar_init(bar_b(FREE, b), 4);
+      for (int cp = 0; cp < 4; ++cp) mbar_init(bar_p(b, cp), 4);  // one arrive per softmax warp of the group
+    }
+    mbar_fence_init();
+  }
+  pdl_launch_dependents();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // prologue done; from here on the previous kernel's output is read
+
+  if (warp == 0) {
+    // ================= TMA producers: lane 0 streams Q/K, lane 1 streams V, up to kA2Stages items ahead ==========
+    if (lane < 2) {
+      for (int k = 0; k < nitems; ++k) {
+        const int st = k & (kA2Stages - 1);
+        const uint32_t ph = (uint32_t)(k / kA2Stages) & 1u;
+        const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
+        const int nk = it.kv_rows > 128 ? 2 : 1;
+        if (lane == 0) {
+          if (k >= kA2Stages) mbar_wait(bar_st(QK_EMPTY, st), ph ^ 1u, 10);  // S of item k-4 has consumed the stage
+          mbar_expect_tx(bar_st(QK_FULL, st), (uint32_t)(kAtQ + nk * 8192));
+          tma_load_2d(sQ(st), &tmQKV, bar_st(QK_FULL, st), it.head * kDh, it.q_row0);
+          tma_load_2d(sK(st), &tmQKV, bar_st(QK_FULL, st), kN + it.head * kDh, it.kv_row0);
+          if (nk == 2) tma_load_2d(sK(st) + 8192, &tmQKV, bar_st(QK_FULL, st), kN + it.head * kDh, it.kv_row0 + 128);
+          stamp(k, 13);
+        } else {
+          if (k >= kA2Stages) mbar_wait(bar_st(V_EMPTY, st), ph ^ 1u, 11);   // PV of item k-4 has consumed the stage
+          mbar_expect_tx(bar_st(V_FULL, st), (uint32_t)(nk * 8192));
+          tma_load_2d(sV(st), &tmQKV, bar_st(V_FULL, st), 2 * kN + it.head * kDh, it.kv_row0);
+          if (nk == 2) tma_load_2d(sV(st) + 8192, &tmQKV, bar_st(V_FULL, st), 2 * kN + it.head * kDh, it.kv_row0 + 128);
+          stamp(k, 14);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= the one tensor-pipe issuer: S = Q K^T and O_c = P_c V_c of both in-flight items ==========
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // A = P from TMEM, B = V MN-major
+      int s_k[2] = {0, 1};   // next item (CTA-local index) whose S goes to TMEM buffer b
+      int p_k[2] = {0, 1};   // item whose PV chunks are being issued on buffer b
+      int p_cp[2] = {0, 0};  // its next chunk
+      int done = 0;
+      long long t_idle = clock64();
+      while (done < nitems) {
+        bool progress = false;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          // ---- S of the next item of this buffer (first: it unblocks a whole softmax group) ----
+          int k = s_k[b];
+          if (k < nitems) {
+            const int st = k & (kA2Stages - 1);
+            const uint32_t ph_st = (uint32_t)(k / kA2Stages) & 1u, ph_b = (uint32_t)(k >> 1) & 1u;
+            if (mbar_test(bar_st(QK_FULL, st), ph_st) && (k < 2 || mbar_test(bar_b(FREE, b), ph_b ^ 1u))) {
+              fence_after();
+              const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
+              const int ncols = (it.kv_rows + 15) & ~15;
+              const uint32_t idesc_s = make_idesc_bf16(128, ncols, 0, 0);
+              const uint64_t ad = make_desc(sQ(st), 512, kLayoutSw64);
+              const uint64_t bd = make_desc(sK(st), 512, kLayoutSw64);
+              const uint32_t d_s = tmem_base + (uint32_t)b * 256;
+              umma_bf16(d_s, ad, bd, idesc_s, 0u);
+              umma_bf16(d_s, ad + 2, bd + 2, idesc_s, 1u);  // second k16 step: +32 B inside the 64-B row
+              umma_commit(bar_b(S_FULL, b));
+              umma_commit(bar_st(QK_EMPTY, st));
+              stamp(k, 0);
+              s_k[b] = k + 2;
+              progress = true;
+            }
+          }
+          // ---- next P_c V_c chunk of the item in flight on this buffer ----
+          k = p_k[b];
+          if (k < nitems && k < s_k[b]) {
+            const int st = k & (kA2Stages - 1);
+            const uint32_t ph_st = (uint32_t)(k / kA2Stages) & 1u, ph_b = (uint32_t)(k >> 1) & 1u;
+            const int cp = p_cp[b];
+            if ((cp > 0 || mbar_test(bar_st(V_FULL, st), ph_st)) && mbar_test(bar_p(b, cp), ph_b)) {
+              fence_after();
+              const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
+              const int ncols = (it.kv_rows + 15) & ~15;
+              const int npair = (ncols + 63) >> 6;
+              const uint32_t t_chunk = tmem_base + (uint32_t)b * 256 + (uint32_t)cp * 64;
+              const int t1 = (cp < npair) ? min(4 * cp + 4, ncols / 16) : 0;
+              for (int t = 4 * cp; t < t1; ++t) {
+                const uint64_t bd = make_desc(sV(st) + (uint32_t)t * 1024, 512, kLayoutSw64);
+                umma_bf16_ts(t_chunk + 32, t_chunk + (uint32_t)(8 * (t & 3)), bd, idesc_pv, (t & 3) != 0 ? 1u : 0u);
+              }
+              stamp(k, 1 + cp);
+              if (cp == 3) {
+                umma_commit(bar_b(O_FULL, b));
+                umma_commit(bar_st(V_EMPTY, st));
+                p_k[b] = k + 2;
+                p_cp[b] = 0;
+                ++done;
+              } else {
+                p_cp[b] = cp + 1;
+              }
+              progress = true;
+            }
+          }
+        }
+        if (progress) {
+          t_idle = clock64();
+        } else if (clock64() - t_idle > 4000000000LL) {
+          printf("attention_tc2: issuer stalled (block %d, S items %d/%d, PV items %d/%d chunks %d/%d, done %d of %d)\n",
+                 (int)blockIdx.x, s_k[0], s_k[1], p_k[0], p_k[1], p_cp[0], p_cp[1], done, nitems);
+          __trap();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue groups (128 threads each, one query row per thread) =================
+    const int grp = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
+    const bool tr = tracing && quarter == 0 && lane == 0;
+    for (int k = grp; k < nitems; k += 2) {
+      const int b = grp;
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
+      const int ncols = (it.kv_rows + 15) & ~15;
+      const int npair = (ncols + 63) >> 6;  // 64-key chunks
+      int lo = 0, hi = it.kv_rows;
+      if (g > 0) {  // packed: this row's own sequence
+        const int sidx = min(r / n, it.q_rows / n - 1);
+        lo = sidx * n;
+        hi = lo + n;
+      }
+      // tcgen05.ld / .st are warp-collective: chunk loops must be warp-uniform, so they run over the union
+      // [wlo, whi) of the key ranges of the warp's 32 rows; per-row masks inside.
+      const int wlo = __reduce_min_sync(0xffffffffu, lo);
+      const int whi = __reduce_max_sync(0xffffffffu, hi);
+      const bool uniform = (g == 0);  // split mode: every row of the tile has the same key range
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
+      if (tr) stamp(k, 5);
+      mbar_wait(bar_b(S_FULL, b), ph, 30);
+      fence_after();
+      if (tr) stamp(k, 6);
+      float m_run = -INFINITY;
+      float mc[4], lc[4];
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        mc[cp] = -INFINITY;
+        lc[cp] = 0.f;
+        if (cp < npair) {
+          const int c0 = cp * 64;
+          uint32_t pk[32];
+          if (c0 + 64 <= wlo || c0 >= whi) {  // warp-uniform: no row of this warp attends these keys
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = 0u;
+          } else {
+            float v[64];
+            tmem_ld64(taddr + c0, v);
+            if (!(uniform && c0 + 64 <= hi)) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
+            }
+            const float m_new = fmaxf(m_run, at_max64(v) * sl2);
+            const float msc = (m_new == -INFINITY) ? 0.f : m_new;  // row has no key yet (packed mode)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {  // FFMA2 for the scale/shift, MUFU.EX2, FADD2 for the row sum
+              fma_f32x2(v[i], v[i + 1], sl2, -msc);
+              fma_f32x2(v[i + 2], v[i + 3], sl2, -msc);
+              v[i] = at_ex2(v[i]);  // masked: 2^-inf = 0
+              v[i + 1] = at_ex2(v[i + 1]);
+              v[i + 2] = at_ex2(v[i + 2]);
+              v[i + 3] = at_ex2(v[i + 3]);
+              add_f32x2(s0, s1, v[i], v[i + 1]);
+              add_f32x2(s2, s3, v[i + 2], v[i + 3]);
+              pk[i >> 1] = cvt_bf16x2(v[i], v[i + 1]);          // column j of P_c = keys (2j, 2j+1)
+              pk[(i >> 1) + 1] = cvt_bf16x2(v[i + 2], v[i + 3]);
+            }
+            mc[cp] = m_new;
+            lc[cp] = (s0 + s1) + (s2 + s3);
+            m_run = m_new;
+          }
+          // P_c over the first half of the chunk's own (already read) score columns; O_c will take the second half
+          tmem_st32(taddr + c0, pk);
+          fence_before();
+        }
+        // (chunks past the item's keys are signalled too: the barrier phases must advance once per item)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p(b, cp));
+        if (tr) stamp(k, 7 + cp);
+      }
+      // ---- epilogue: O = sum_c 2^(m_c - m) O_c, row sum likewise, O / rowsum -> bf16 ----
+      float fc[4], sum = 0.f;
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        fc[cp] = (mc[cp] == -INFINITY) ? 0.f : at_ex2(mc[cp] - m_run);
+        sum += fc[cp] * lc[cp];
+      }
+      mbar_wait(bar_b(O_FULL, b), ph, 31);
+      fence_after();
+      if (tr) stamp(k, 11);
+      {
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int cp = 0; cp < 4; ++cp) {
+          if (cp < npair) {
+            float oc[32];
+            tmem_ld32(taddr + cp * 64 + 32, oc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = fmaf(fc[cp], oc[i], o[i]);
+          }
+        }
+        fence_before();  // O_c reads precede the next S overwriting the buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_b(FREE, b));  // release TMEM before the global stores
+        const float inv = 1.0f / sum;
+        if (r < it.q_rows) {
+          uint4* dsto = reinterpret_cast<uint4*>(out + (size_t)(it.q_row0 + r) * kN + it.head * kDh);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = cvt_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv);
+            u.y = cvt_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+            u.z = cvt_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+            u.w = cvt_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+            dsto[i] = u;
+          }
+        }
+      }
+      if (tr) stamp(k, 12);
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -386,15 +700,29 @@ static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
   return 0;
 }
 
+// CSE_ATTN_V2=0 keeps the v1 kernel (two issuer warps, P through shared memory) for A/B runs.
+static bool attention_v2_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_ATTN_V2");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+long long* g_attention_trace = nullptr;  // cse_debug_attention_trace: device buffer [64 items][16 slots] of clock64 stamps
+
 int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_t st) {
   if (n < 1 || n > 256) {
     set_error("attention_tc: n=%d outside [1,256]", n);
     return 1;
   }
+  const bool v2 = g_attention_mode == 3 || (g_attention_mode != 2 && attention_v2_enabled());
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAtSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return 1;
@@ -412,6 +740,11 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     return 1;
   }
   const int grid = (int)(items < sms ? items : sms);
+  if (v2) {
+    launch_pdl(attention_tc2_kernel, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g, (int)items,
+               g_attention_trace);
+    return check_launch("attention_tc2_kernel");
+  }
   launch_pdl(attention_tc_kernel, dim3(grid), dim3(kAtThreads), kAtSmem, st, 1, tm, out, n, nseq, g, (int)items);
   return check_launch("attention_tc_kernel");
 }

@@ -114,6 +114,9 @@ CSE_API long long cse_launch_count(void);
 /* Test hook: 0 = automatic choice, 1 = force the mma.sync online-softmax bf16 attention kernel,
  * 2 = force the tcgen05 kernel (n <= 256) — so both kernels can be checked at the same shapes. */
 CSE_API int cse_debug_force_mma_attention(int on);
+/* Debug: device buffer of 64 x 16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64 stamps of its
+ * pipeline events (tools/attn_trace.py); NULL turns it off. */
+CSE_API int cse_debug_attention_trace(long long* device_buffer);
 /* Optional device timing per kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 fp32 SIMT
  * GEMM): while enabled, each launch of those classes is bracketed by a CUDA event pair on its
  * stream; cse_profile_collect sums and clears them (synchronises on the recorded events). */

@@ -8,7 +8,7 @@ Three independent yardsticks, each on the same seeded inputs:
   * the CPU oracle run LIVE on the box (fp32, `oracle/sepformer_oracle.py`);
   * `tests/golden/baseline_*.npz` — the reference's own modules' fp32 output and its own bf16-autocast (CPU) output,
     written by `tests/golden/make_golden_baseline.py` in the authoring container;
-  * `tools/eager_yardstick.py` — the reference's op sequence on stock torch CUDA kernels: validated here against the
+  * `oracle/eager_reference.py` — the reference's op sequence on stock torch CUDA kernels: validated here against the
     oracle in fp32, then its CUDA bf16-autocast + flash-SDPA run (the reference's real --bf16 arithmetic,
     train_ContSep.py:383) is the drift yardstick the CPU-autocast fixture could only approximate.
 
@@ -27,7 +27,6 @@ Tolerances (BASELINE.json north_star):
 """
 import math
 import os
-import sys
 
 import pytest
 import torch
@@ -39,9 +38,7 @@ from helpers import load_golden, rel_l2
 from oracle import sepformer_oracle as O
 from test_forward_gpu import build_model, si_snr_db
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
-import eager_yardstick as EY  # noqa: E402
+from oracle import eager_reference as EY
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -173,7 +170,7 @@ def test_cfg2_fp32_every_mixture_vs_live_oracle_and_reference_fixture(cfg2):
 
 
 def test_cfg2_eager_yardstick_is_the_same_function(cfg2):
-    """tools/eager_yardstick.py in true fp32 on the GPU == the oracle: it is a valid drift / speed yardstick."""
+    """oracle/eager_reference.py in true fp32 on the GPU == the oracle: it is a valid drift / speed yardstick."""
     c = cfg2
     est, pred = _eager(c["m"], c["case"], c["mix"][:4], c["ctx"][:4], None, "fp32")
     assert rel_l2(est, c["ref_est"][:4]) < 2e-5

@@ -234,3 +234,79 @@ def test_errors_are_python_exceptions():
         m(torch.zeros(1, 4000))                           # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         m.decoder(torch.zeros(1, 1, 256, 10, device=DEV))  # speechbrain Decoder's own check
+
+
+def test_host_pipeline_matches_blocking_entry():
+    """cse_pipeline_* (2 forwards in flight, graph replay, copies on their own streams) returns bit-identical
+    results to cse_forward_host for a stream of different batches, in submission order."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_b2_t4000")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    for prec in ("bf16", "fp32"):
+        m.precision = prec
+        batches = [(mix.roll(i, 1) * (1.0 - 0.1 * i)).contiguous().pin_memory() for i in range(5)]
+        ctxs = [(ctx * (1.0 + 0.05 * i)).contiguous().pin_memory() for i in range(5)]
+        want = [m.separate_host(b, c) for b, c in zip(batches, ctxs)]
+        want = [(e.clone(), p.clone()) for e, p in want]
+        pipe = m.host_pipeline(2, 4000, c=1, depth=2)
+        tickets, got = [], []
+        for i, (b, c) in enumerate(zip(batches, ctxs)):
+            tickets.append(pipe.submit(b, c))
+            if i >= 1:                                       # keep two in flight
+                e, p = pipe.wait(tickets[i - 1])
+                got.append((e.clone(), p.clone()))
+        e, p = pipe.wait(tickets[-1])
+        got.append((e.clone(), p.clone()))
+        pipe.close()
+        for (e0, p0), (e1, p1) in zip(want, got):
+            assert torch.equal(e0, e1) and torch.equal(p0, p1)
+    with pytest.raises(RuntimeError):
+        m.host_pipeline(2, 4000, c=1, depth=2).submit(mix, ctx.pin_memory())      # unpinned host buffer
+
+
+def test_inference_mode_and_fp16_autocast():
+    """torch.inference_mode (test_cascaded.py:146) works; fp16 autocast (the README's --fp16 default, README.md:142)
+    maps to the same bf16 tensor-core kernels as --bf16 (differences): bit-identical outputs."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_b2_t4000")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.precision = "fp32"
+    est0, pred0 = run_model(m, meta, mix, ctx, se)
+    with torch.inference_mode():
+        est1, pred1 = m(mix.to(DEV), ctx.to(DEV))
+    assert torch.equal(est0, est1) and torch.equal(pred0, pred1)
+    m.precision = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        e_bf, _ = run_model(m, meta, mix, ctx, se)
+    with torch.autocast("cuda", dtype=torch.float16):
+        e_fp, _ = run_model(m, meta, mix, ctx, se)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.float16):
+        e_im, _ = m(mix.to(DEV), ctx.to(DEV))
+    assert e_fp.dtype == torch.float32 and torch.equal(e_bf, e_fp) and torch.equal(e_bf, e_im)
+    assert rel_l2(e_bf.cpu(), load_golden("contsep_2spk_b2_t4000")["est"]) < BF16_REL_TOL
+
+
+def test_second_call_shape_and_parameter_reallocation_with_graphs():
+    """The graph cache is keyed on the parameter-table generation: re-allocating the parameters (`.to()`,
+    add_ctx after a first call) drops every captured graph instead of replaying stale pointers."""
+    sd, mix, src, ctx, se, meta = model_case("contsep_2spk_b2_t4000")
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.precision = "bf16"
+    m.use_cuda_graph = True
+    est0, _ = run_model(m, meta, mix, ctx, se)
+    gen0 = m._table.generation
+    for p in m.parameters():                       # new storages, same values
+        p.data = p.data.clone()
+    est1, _ = run_model(m, meta, mix, ctx, se)
+    assert m._table.generation == gen0 + 1 and torch.equal(est0, est1)
+    with torch.no_grad():
+        m.encoder.conv1d.weight.mul_(2.0)          # in-place update: same pointers, new version -> re-pack, same graph
+    est2, _ = run_model(m, meta, mix, ctx, se)
+    assert not torch.equal(est2, est1)
+    for T in (3000, 3008, 3016, 3024, 3032):       # more shapes than the LRU keeps
+        run_model(m, meta, mix[:, :T].contiguous(), ctx, se)
+    assert len(m._graphs) <= m.max_cached_graphs

@@ -116,3 +116,23 @@ def test_oracle_matches_reference_at_baseline_shapes(name):
         assert est.shape == fix["est"].shape and rel_l2(est, fix["est"]) < 2e-5
     if pred is not None:
         assert rel_l2(pred, fix["context_pred"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["contsep_2spk_b2_t4000", "hcontext_3spk_joint_b2_t2500", "sepformer_2spk_b1_t4003",
+                                  "contsep_2spk_bce_b1_t2024", "hcontext_2spk_voice_b1_t1999", "context_2spk_c3_b1_t2000"])
+def test_eager_reference_is_bit_identical_to_the_reference_fixtures(name):
+    """oracle/eager_reference.py (the reference's op sequence on stock torch modules; bench.py's CPU baseline and the
+    GPU-eager yardstick) reproduces the reference modules' own fp32 outputs exactly on CPU."""
+    from oracle import eager_reference as EY
+    from test_forward_gpu import build_model
+    sd, mix, src, ctx, se, meta = model_case(name)
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m.eval()
+    with torch.no_grad():
+        out = EY.eager_forward(m, mix, ctx, se, meta["cue"] or "joint")
+    gold = load_golden(name)
+    est, pred = out if isinstance(out, tuple) else (out, None)
+    assert torch.equal(est, gold["est"])
+    if pred is not None:
+        assert torch.equal(pred, gold["context_pred"])

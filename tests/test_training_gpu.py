@@ -300,3 +300,43 @@ def test_training_step_updates_parameters_like_the_oracle():
                     v -= 1e-3 * g
         ref_vals.append(loss.item())
     assert abs(vals[0] - ref_vals[0]) < 2e-3 and abs(vals[1] - ref_vals[1]) < 5e-3, (vals, ref_vals)
+
+
+@pytest.mark.parametrize("name,loss_fn,fixture", [
+    ("context_2spk_b2_t3000", _loss_context, "grad_context_2spk_b2_t3000"),
+    ("contsep_2spk_bce_b1_t2024", _loss_contsep, "grad_contsep_2spk_bce_b1_t2024"),
+])
+@pytest.mark.parametrize("amp_dtype", [torch.bfloat16, torch.float16])
+def test_autocast_training_step_carries_a_graph_and_stays_within_reference_drift(name, loss_fn, fixture, amp_dtype):
+    """The reference's actual training mode (train_ContSep.py:383-400, README.md:142: forward + loss under
+    torch.autocast, scaler.scale(loss).backward()): the drop-in must return outputs WITH an autograd graph, and
+    the gradients of the bf16 tensor-core path may drift from the fp32 gradients by no more than the reference's
+    own autocast step does on the same fixture (`bf16_ref_global_rel_l2`, make_golden_grads.py)."""
+    from helpers import load_golden
+    sd, mix, src, ctx, se, meta = model_case(name)
+    m = build_model(meta)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    scaler = torch.amp.GradScaler("cuda", enabled=(amp_dtype == torch.float16))
+    with torch.autocast("cuda", dtype=amp_dtype):
+        out = m(mix.to(DEV), ctx.to(DEV))
+        first = out[0] if isinstance(out, tuple) else out
+        assert first.requires_grad and first.grad_fn is not None, "autocast training output carries no graph"
+        loss = loss_fn(out, src.to(DEV), None)
+    scaler.scale(loss).backward()
+    torch.cuda.synchronize()
+    inv = 1.0 / scaler.get_scale() if amp_dtype == torch.float16 else 1.0
+    ref_loss, ref = _reference_grads(sd, mix, src, ctx, se, meta, loss_fn)
+    got = {k: p.grad * inv for k, p in m.named_parameters() if p.grad is not None}
+    missing = [k for k in ref if k not in got and ref[k].abs().max() > 0]
+    assert not missing, missing
+    num = sum(((got[k].cpu().double() - ref[k]) ** 2).sum() for k in ref if k in got)
+    den = sum((ref[k] ** 2).sum() for k in ref if k in got)
+    drift = (num / den).sqrt().item()
+    fix = load_golden(fixture)
+    bar = float(fix["bf16_ref_global_rel_l2"])
+    print(f"\n[autocast {amp_dtype} {name}] loss {loss.item():.4f} (fp64 oracle {ref_loss:.4f}, reference bf16 "
+          f"{float(fix['bf16_ref_loss']):.4f}); global gradient drift {drift:.3e} vs the reference's own autocast drift {bar:.3e}")
+    assert all(torch.isfinite(g).all() for g in got.values())
+    assert drift <= bar
+    assert abs(loss.item() - ref_loss) <= max(0.05, 1.5 * abs(float(fix["bf16_ref_loss"]) - float(fix["loss"])))
