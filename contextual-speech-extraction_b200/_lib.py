@@ -93,6 +93,9 @@ _SIGNATURES = {
     "cse_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v]),
     "cse_pit_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
     "cse_tm_si_snr": (C.c_int, [_v, _v, C.c_int, C.c_int, _v, _v]),
+    "cse_selection_loss": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, C.c_int, C.c_int, _v, _v, _v, _v, _v, _v]),
+    "cse_select_stream": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
+    "cse_selection_accuracy": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
     "cse_si_snr_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
     "cse_pit_si_snr_bwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, C.c_int, _v, _v, _v]),
     "cse_tm_si_snr_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v, _v]),

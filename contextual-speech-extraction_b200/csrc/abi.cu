@@ -767,4 +767,28 @@ int cse_tm_si_snr(const float* preds, const float* target, int B, int T, float* 
   return launch_tm_si_snr(preds, target, B, T, out, (cudaStream_t)stream);
 }
 
+// ---- ContSep selection tail ----
+int cse_selection_loss(const float* gt, const float* est, const float* logits, int B, int T, int n_streams,
+                       int ce, float* sisnr, long long* label, float* loss, float* dlogits, float* item_loss,
+                       void* stream) {
+  CSE_REQUIRE(gt && est && logits && sisnr && label && loss && dlogits && item_loss && B > 0 && T > 0,
+              "selection_loss: bad argument");
+  CSE_REQUIRE(ce || n_streams == 2, "selection_loss: the single-logit BCE head exists for 2 streams only (ContSep.py:46-51)");
+  return launch_selection_loss(gt, est, logits, B, T, n_streams, ce, sisnr, label, item_loss, loss, dlogits,
+                               (cudaStream_t)stream);
+}
+
+int cse_select_stream(const float* est, const float* logits, int B, int T, int n_streams, int ce, float* out,
+                      long long* pick, void* stream) {
+  CSE_REQUIRE(est && logits && out && pick && B > 0 && T > 0 && n_streams >= 1, "select_stream: bad argument");
+  CSE_REQUIRE(ce || n_streams == 2, "select_stream: the single-logit head exists for 2 streams only");
+  return launch_select_stream(est, logits, B, T, n_streams, ce, out, pick, (cudaStream_t)stream);
+}
+
+int cse_selection_accuracy(const float* enhanced, const float* sources, int B, int T, int n_sources, float* sisnr,
+                           int* acc, void* stream) {
+  CSE_REQUIRE(enhanced && sources && sisnr && acc && B > 0 && T > 0, "selection_accuracy: bad argument");
+  return launch_selection_accuracy(enhanced, sources, B, T, n_sources, sisnr, acc, (cudaStream_t)stream);
+}
+
 }  // extern "C"

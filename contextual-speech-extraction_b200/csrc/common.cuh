@@ -246,6 +246,13 @@ int launch_si_snr_bwd(const float* source, const float* estimate, int B, int T, 
                       cudaStream_t st);
 int launch_tm_si_snr_bwd(const float* preds, const float* target, int B, int T, const float* gout,
                          float* d_preds, float* d_target, cudaStream_t st);
+int launch_selection_loss(const float* gt, const float* est, const float* logits, int B, int T, int C, int ce,
+                          float* sisnr, long long* label, float* item_loss, float* loss, float* dlogits,
+                          cudaStream_t st);
+int launch_select_stream(const float* est, const float* logits, int B, int T, int C, int ce, float* out,
+                         long long* pick, cudaStream_t st);
+int launch_selection_accuracy(const float* enhanced, const float* sources, int B, int T, int C, float* sisnr,
+                              int* acc, cudaStream_t st);
 // backward.cu (fp32 training path)
 int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st);
 int launch_wgrad(const float* X, int ldx, const float* Y, int ldy, int M, int N1, int N2, float* dW,

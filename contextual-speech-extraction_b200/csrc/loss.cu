@@ -360,4 +360,203 @@ int launch_tm_si_snr(const float* preds, const float* target, int B, int T, floa
   return check_launch("tm_si_snr_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// ContSep selection tail: the immediate consumer of `est` / `context_pred`.
+//   training (train_ContSep.py:386-388): per-stream SI-SNR of the estimate against the ground truth ->
+//     label = argmax -> CrossEntropy / BCEWithLogits of the selector logits (estimate detached);
+//   eval (test.py:234-239, 248-255): pick the stream the selector chose, and the "was it the right one"
+//     accuracy bit (SI-SNR against the target >= SI-SNR against every interferer).
+// The reference does these with ~25 tiny ATen launches and three host round trips (`.cpu()` at test.py:236);
+// here each is one CTA per item over the same one-pass sufficient statistics as the losses above.
+// ---------------------------------------------------------------------------------------------
+
+// x [T] against the C columns of y [T,C]: sums {x, x^2, y_j, y_j^2, x y_j} in double.  Valid in thread 0.
+struct OneManyStats {
+  double sx, sxx, sy[kMaxC], syy[kMaxC], sxy[kMaxC];
+};
+
+template <int C>
+__device__ void one_vs_many_stats(const float* __restrict__ x, const float* __restrict__ y, int T, OneManyStats& out) {
+  constexpr int NV = 2 + 3 * C;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (int t = threadIdx.x; t < T; t += kLossThreads) {
+    const double xv = (double)x[t];
+    acc[0] += xv;
+    acc[1] += xv * xv;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const double yv = (double)y[(size_t)t * C + j];
+      acc[2 + j] += yv;
+      acc[2 + C + j] += yv * yv;
+      acc[2 + 2 * C + j] += xv * yv;
+    }
+  }
+  __shared__ double s_red[kLossThreads / 32][NV];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[wid][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double v = 0.0;
+      for (int w = 0; w < kLossThreads / 32; ++w) v += s_red[w][i];
+      acc[i] = v;
+    }
+    out.sx = acc[0];
+    out.sxx = acc[1];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      out.sy[j] = acc[2 + j];
+      out.syy[j] = acc[2 + C + j];
+      out.sxy[j] = acc[2 + 2 * C + j];
+    }
+  }
+}
+
+// speechbrain cal_si_snr from centred statistics: ss = |source~|^2, ee = |estimate~|^2, dot = <e~, s~>
+__device__ double sb_neg_si_snr_centred(double ss, double ee, double dot) {
+  const double eps = 1e-8;
+  const double energy = ss + eps;
+  const double proj2 = dot * dot * ss / (energy * energy);
+  double noise2 = ee - 2.0 * dot * dot / energy + proj2;
+  if (noise2 < 0.0) noise2 = 0.0;
+  return -10.0 * log10(proj2 / (noise2 + eps) + eps);
+}
+
+// torch.argmax semantics: first maximum; a NaN counts as the maximum
+__device__ int argmax_first(const float* v, int n) {
+  int best = 0;
+  for (int i = 1; i < n; ++i) {
+    const bool better = (v[i] > v[best]) || (isnan(v[i]) && !isnan(v[best]));
+    if (better) best = i;
+  }
+  return best;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLossThreads) selection_loss_kernel(
+    const float* __restrict__ gt, const float* __restrict__ est, const float* __restrict__ logits, int T, int ce,
+    int B, float* __restrict__ sisnr, long long* __restrict__ label, float* __restrict__ item_loss,
+    float* __restrict__ dlogits) {
+  __shared__ OneManyStats st;
+  const size_t b = blockIdx.x;
+  one_vs_many_stats<C>(gt + b * T, est + b * T * C, T, st);
+  if (threadIdx.x != 0) return;
+  const double n = (double)T;
+  const double ss = st.sxx - st.sx * st.sx / n;              // source = ground truth
+  float v[C];
+  for (int j = 0; j < C; ++j) {
+    const double ee = st.syy[j] - st.sy[j] * st.sy[j] / n;
+    const double dot = st.sxy[j] - st.sx * st.sy[j] / n;
+    v[j] = (float)(-sb_neg_si_snr_centred(ss, ee, dot));     // sisnrs = -1 * cal_si_snr(...)
+    sisnr[b * C + j] = v[j];
+  }
+  const int y = argmax_first(v, C);
+  label[b] = y;
+  const float inv_b = 1.0f / (float)B;
+  if (ce) {                                                  // nn.CrossEntropyLoss (mean over the batch)
+    const float* z = logits + b * C;
+    float m = z[0];
+    for (int j = 1; j < C; ++j) m = fmaxf(m, z[j]);
+    float se = 0.f;
+    for (int j = 0; j < C; ++j) se += expf(z[j] - m);
+    const float lse = m + logf(se);
+    item_loss[b] = lse - z[y];
+    for (int j = 0; j < C; ++j) dlogits[b * C + j] = (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * inv_b;
+  } else {                                                   // nn.BCEWithLogitsLoss on the single logit, target = label
+    const float z = logits[b], t = (float)y;
+    item_loss[b] = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+    dlogits[b] = (1.f / (1.f + expf(-z)) - t) * inv_b;
+  }
+}
+
+__global__ void mean_in_order_kernel(const float* __restrict__ item, int B, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += item[b];                // fixed order: deterministic
+    out[0] = s / (float)B;
+  }
+}
+
+// pick = argmax softmax(logits) (== argmax logits) or sigmoid(logit) > 0.5 (== logit > 0); out[b,t] = est[b,t,pick[b]]
+__global__ void __launch_bounds__(256) select_stream_kernel(const float* __restrict__ est,
+                                                            const float* __restrict__ logits, int T, int C, int ce,
+                                                            float* __restrict__ out, long long* __restrict__ pick) {
+  const size_t b = blockIdx.y;
+  int p;
+  if (ce) {
+    p = argmax_first(logits + b * C, C);
+  } else {
+    p = logits[b] > 0.f ? 1 : 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) pick[b] = p;
+  const float* e = est + b * T * C + p;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) out[b * T + t] = e[(size_t)t * C];
+}
+
+// enhanced [T] is the ESTIMATE, the columns of sources [T,C] are the sources (column 0 = target, others = interferers)
+template <int C>
+__global__ void __launch_bounds__(kLossThreads) selection_accuracy_kernel(const float* __restrict__ enhanced,
+                                                                          const float* __restrict__ sources, int T,
+                                                                          float* __restrict__ sisnr,
+                                                                          int* __restrict__ acc) {
+  __shared__ OneManyStats st;
+  const size_t b = blockIdx.x;
+  one_vs_many_stats<C>(enhanced + b * T, sources + b * T * C, T, st);
+  if (threadIdx.x != 0) return;
+  const double n = (double)T;
+  const double ee = st.sxx - st.sx * st.sx / n;
+  float v[C];
+  for (int j = 0; j < C; ++j) {
+    const double ss = st.syy[j] - st.sy[j] * st.sy[j] / n;
+    const double dot = st.sxy[j] - st.sx * st.sy[j] / n;
+    v[j] = (float)(-sb_neg_si_snr_centred(ss, ee, dot));
+    sisnr[b * C + j] = v[j];
+  }
+  int ok = 1;
+  for (int j = 1; j < C; ++j) ok *= (v[0] >= v[j]) ? 1 : 0;   // test.py:251-255
+  acc[b] = ok;
+}
+
+int launch_selection_loss(const float* gt, const float* est, const float* logits, int B, int T, int C, int ce,
+                          float* sisnr, long long* label, float* item_loss, float* loss, float* dlogits,
+                          cudaStream_t st) {
+  switch (C) {
+    case 2: selection_loss_kernel<2><<<B, kLossThreads, 0, st>>>(gt, est, logits, T, ce, B, sisnr, label, item_loss, dlogits); break;
+    case 3: selection_loss_kernel<3><<<B, kLossThreads, 0, st>>>(gt, est, logits, T, ce, B, sisnr, label, item_loss, dlogits); break;
+    case 4: selection_loss_kernel<4><<<B, kLossThreads, 0, st>>>(gt, est, logits, T, ce, B, sisnr, label, item_loss, dlogits); break;
+    default: set_error("selection_loss: %d streams unsupported (2..%d)", C, kMaxC); return 1;
+  }
+  if (check_launch("selection_loss_kernel")) return 1;
+  mean_in_order_kernel<<<1, 32, 0, st>>>(item_loss, B, loss);
+  return check_launch("mean_in_order_kernel");
+}
+
+int launch_select_stream(const float* est, const float* logits, int B, int T, int C, int ce, float* out,
+                         long long* pick, cudaStream_t st) {
+  dim3 grid((unsigned)min(ceil_div(T, 256), 148), (unsigned)B);
+  select_stream_kernel<<<grid, 256, 0, st>>>(est, logits, T, C, ce, out, pick);
+  return check_launch("select_stream_kernel");
+}
+
+int launch_selection_accuracy(const float* enhanced, const float* sources, int B, int T, int C, float* sisnr,
+                              int* acc, cudaStream_t st) {
+  switch (C) {
+    case 1: selection_accuracy_kernel<1><<<B, kLossThreads, 0, st>>>(enhanced, sources, T, sisnr, acc); break;
+    case 2: selection_accuracy_kernel<2><<<B, kLossThreads, 0, st>>>(enhanced, sources, T, sisnr, acc); break;
+    case 3: selection_accuracy_kernel<3><<<B, kLossThreads, 0, st>>>(enhanced, sources, T, sisnr, acc); break;
+    case 4: selection_accuracy_kernel<4><<<B, kLossThreads, 0, st>>>(enhanced, sources, T, sisnr, acc); break;
+    default: set_error("selection_accuracy: %d sources unsupported (1..%d)", C, kMaxC); return 1;
+  }
+  return check_launch("selection_accuracy_kernel");
+}
+
 }  // namespace cse

@@ -294,6 +294,24 @@ CSE_API int cse_pit_si_snr(const float* source, const float* estimate_source, in
 CSE_API int cse_tm_si_snr(const float* preds, const float* target, int B, int T,
                           float* out, void* stream);
 
+/* ---- ContSep selection tail (estimate tensors are [B,T,n_streams] as the model returns them) ---- */
+/* Training (train_ContSep.py:386-388): sisnr[b,s] = -cal_si_snr(source = gt[b], estimate = est[b,:,s]) (estimate
+ * detached), label[b] = argmax_s (first maximum, int64), loss[0] = CrossEntropyLoss(logits [B,n_streams], label)
+ * when ce != 0, else BCEWithLogitsLoss(logits [B] (the single-logit head, 2 streams), label.float()); both batch
+ * means.  dlogits (same shape as logits) = d loss / d logits, so the backward pass is a scale by the incoming
+ * gradient.  item_loss: B floats of scratch.  One launch per item + a fixed-order mean: no host round trip. */
+CSE_API int cse_selection_loss(const float* gt, const float* est, const float* logits, int B, int T,
+                               int n_streams, int ce, float* sisnr, long long* label, float* loss,
+                               float* dlogits, float* item_loss, void* stream);
+/* Eval (test.py:234-239): pick[b] = argmax softmax(logits[b]) (ce) or sigmoid(logit[b]) > 0.5, out[b,:] =
+ * est[b,:,pick[b]] — the reference moves the logits to the host for this (`ctx_pred.cpu()`, test.py:236). */
+CSE_API int cse_select_stream(const float* est, const float* logits, int B, int T, int n_streams, int ce,
+                              float* out, long long* pick, void* stream);
+/* Eval (test.py:248-255): sisnr[b,j] = -cal_si_snr(source = sources[b,:,j], estimate = enhanced[b]);
+ * acc[b] = 1 iff sisnr[b,0] >= sisnr[b,j] for every interferer j >= 1 (column 0 = the target speaker). */
+CSE_API int cse_selection_accuracy(const float* enhanced, const float* sources, int B, int T, int n_sources,
+                                   float* sisnr, int* acc, void* stream);
+
 /* ---- backward (training step, BASELINE configs[2]) ----
  * The reference trains through autograd (`loss.backward()`, train_ContSep.py:402-419,
  * train_ContExt.py:372-389); these entry points are the hand-written gradients of the same

@@ -60,3 +60,28 @@ def baseline_inputs(case):
     se = synth.make_speaker_embedding(B, seed=case["iseed"]) if case["variant"] == "hcontext" else None
     sl = slice(i, i + 1)
     return mix[sl].contiguous(), src[sl].contiguous(), ctx[sl].contiguous(), (None if se is None else se[sl].contiguous())
+
+# ContSep selection tail (make_golden_selection.py).
+SELECTION_CASES = {
+    "selection_ce_2spk_b4_t4000": dict(spk=2, ce=True, B=4, T=4000, seed=51),
+    "selection_bce_2spk_b3_t3001": dict(spk=2, ce=False, B=3, T=3001, seed=52),
+    "selection_ce_3spk_b5_t2500": dict(spk=3, ce=True, B=5, T=2500, seed=53),
+}
+
+
+def selection_inputs(case):
+    """(gt [B,T], interferers [B,T,spk-1], est [B,T,spk], ctx_pred [B,spk | 1]): estimates are imperfect mixtures of
+    the sources in a per-item random stream order, logits are seeded noise."""
+    import torch
+    from cse_b200 import synth
+    B, T, n = case["B"], case["T"], case["spk"]
+    _, src = synth.make_mixture(B, T, max(n, 2), seed=case["seed"])
+    g = torch.Generator().manual_seed(case["seed"])
+    est = torch.empty(B, T, n)
+    for b in range(B):
+        perm = torch.randperm(n, generator=g)
+        for s in range(n):
+            other = src[b, :, perm[(s + 1) % n]]
+            est[b, :, s] = 0.7 * src[b, :, perm[s]] + 0.3 * other + 0.05 * torch.randn(T, generator=g)
+    ctx_pred = torch.randn(B, n if case["ce"] else 1, generator=g) * 2.0
+    return src[:, :, 0].contiguous(), src[:, :, 1:n].contiguous(), est.contiguous(), ctx_pred
