@@ -18,7 +18,8 @@ def rel_l2(a, b):
 
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
-        return {k: torch.from_numpy(z[k]) for k in z.files}
+        # (string-typed entries, e.g. the parameter-name lists of the gradient fixtures, stay numpy arrays)
+        return {k: (torch.from_numpy(z[k]) if z[k].dtype.kind in "fiub" else z[k]) for k in z.files}
 
 
 def model_case(name):
