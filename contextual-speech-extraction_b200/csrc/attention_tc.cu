@@ -336,18 +336,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// v2: same arithmetic, re-plumbed so that the MUFU (softmax) and tensor-pipe (S, PV) phases of the two items in
-// flight overlap instead of adding up (profiles/r01_ncu_full_layer.txt: 260 k cycles per launch = 122 k cycles of
-// MUFU.EX2 + ~140 k cycles of N = 32 / N = 256 UMMAs issued back to back):
-//   * ONE issuing warp polls (mbarrier.test_wait) every pending piece of tensor work of both in-flight items and
-//     issues whichever is ready — S of the next item first.  v1's PV warp walked the items in order, so the four PV
-//     chunks of item k+1 queued behind the last softmax chunk of item k, and S of item k+2 queued behind those.
-//   * P never touches shared memory: the bf16 probabilities go back into the item's own consumed score columns
-//     (tcgen05.st) and feed P_c V_c as the TMEM A operand; O_c lands beside them.  No generic->async proxy fence,
-//     no swizzled STS, and the 128 KB of P staging become a 4-deep Q/K/V ring, so V is resident long before its
-//     first P_c V_c instead of being requested when the previous item on the buffer finishes.
+// v3.  What bounded v1 (and a first re-plumbing, "v2", that kept its arithmetic) was not MUFU and not the issue
+// order but the tensor pipe itself: a tcgen05.mma that OVERWRITES its accumulator (scale-d = 0) costs ~775 cycles
+// at M = 128 whatever N is, against ~105 for one that accumulates (tools/micro/umma_pv_rate.cu, B200: groups of
+// "1 overwrite + 3 accumulate" average 273 cycles per instruction, pure accumulate chains 105).  The online softmax
+// gave every 64-key chunk its own O_c accumulator, i.e. 4 overwriting instructions + 1 for S per item: ~4.4 k of
+// the ~4.8 k cycles an item took.  v3 therefore
+//   * takes the row maximum over the WHOLE score row first (a second tcgen05.ld pass over S is ~150 cycles per
+//     item), so every P_c is exponentiated against the final maximum and all sixteen P_c V_c instructions
+//     ACCUMULATE into one O tile that the softmax warps zero-fill with tcgen05.st;
+//   * (ZERO_S) lets the softmax warps zero-fill the score columns as well, so that Q K^T accumulates too;
+//   * keeps v2's plumbing: ONE issuing warp polls (mbarrier.test_wait) every pending piece of tensor work of both
+//     in-flight items and issues whichever is ready, S of the next item first; P never touches shared memory (bf16
+//     pairs go back into the item's own consumed score columns and feed P_c V_c as the TMEM A operand), and the
+//     128 KB of P staging v1 needed are a 4-deep Q/K/V ring.
 // TMEM columns of buffer b (256 per item): chunk c (64 keys) = [64c, 64c+64): scores -> P_c in [64c, 64c+32)
-// (two bf16 per column), O_c (fp32 [128 x 32]) in [64c+32, 64c+64).
+// (two bf16 per column); O (fp32 [128 x 32]) in [32, 64), the dead upper half of chunk 0.
 // ------------------------------------------------------------------------------------------
 constexpr int kA2Threads = 320;  // warp 0 TMA, warp 1 S/PV issuer, warps 2-5 softmax group 0, warps 6-9 group 1
 constexpr int kA2Stages = 4;
@@ -367,8 +371,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // n
   return ok != 0;
 }
 
+template <bool ZERO_S>
 __global__ void __launch_bounds__(kA2Threads, 1)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
                      int g, int items, long long* __restrict__ trace) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -443,7 +448,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= the one tensor-pipe issuer: S = Q K^T and O_c = P_c V_c of both in-flight items ==========
+    // ================= the one tensor-pipe issuer: S = Q K^T and O += P_c V_c of both in-flight items ==========
     if (lane == 0) {
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // A = P from TMEM, B = V MN-major
       int s_k[2] = {0, 1};   // next item (CTA-local index) whose S goes to TMEM buffer b
@@ -460,7 +465,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
           if (k < nitems) {
             const int st = k & (kA2Stages - 1);
             const uint32_t ph_st = (uint32_t)(k / kA2Stages) & 1u, ph_b = (uint32_t)(k >> 1) & 1u;
-            if (mbar_test(bar_st(QK_FULL, st), ph_st) && (k < 2 || mbar_test(bar_b(FREE, b), ph_b ^ 1u))) {
+            // FREE completes once per item (its O has been read out) — and, with ZERO_S, once more at kernel start
+            // (the group's first zero-fill), so use j of the buffer waits for completion j instead of j - 1
+            const bool buf_free = ZERO_S ? mbar_test(bar_b(FREE, b), ph_b) : (k < 2 || mbar_test(bar_b(FREE, b), ph_b ^ 1u));
+            if (buf_free && mbar_test(bar_st(QK_FULL, st), ph_st)) {
               fence_after();
               const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
               const int ncols = (it.kv_rows + 15) & ~15;
@@ -468,7 +476,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
               const uint64_t ad = make_desc(sQ(st), 512, kLayoutSw64);
               const uint64_t bd = make_desc(sK(st), 512, kLayoutSw64);
               const uint32_t d_s = tmem_base + (uint32_t)b * 256;
-              umma_bf16(d_s, ad, bd, idesc_s, 0u);
+              umma_bf16(d_s, ad, bd, idesc_s, ZERO_S ? 1u : 0u);
               umma_bf16(d_s, ad + 2, bd + 2, idesc_s, 1u);  // second k16 step: +32 B inside the 64-B row
               umma_commit(bar_b(S_FULL, b));
               umma_commit(bar_st(QK_EMPTY, st));
@@ -488,11 +496,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
               const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
               const int ncols = (it.kv_rows + 15) & ~15;
               const int npair = (ncols + 63) >> 6;
-              const uint32_t t_chunk = tmem_base + (uint32_t)b * 256 + (uint32_t)cp * 64;
+              const uint32_t t_buf = tmem_base + (uint32_t)b * 256;
               const int t1 = (cp < npair) ? min(4 * cp + 4, ncols / 16) : 0;
               for (int t = 4 * cp; t < t1; ++t) {
                 const uint64_t bd = make_desc(sV(st) + (uint32_t)t * 1024, 512, kLayoutSw64);
-                umma_bf16_ts(t_chunk + 32, t_chunk + (uint32_t)(8 * (t & 3)), bd, idesc_pv, (t & 3) != 0 ? 1u : 0u);
+                // every instruction accumulates: the softmax warps zero-filled O before signalling chunk 0
+                umma_bf16_ts(t_buf + 32, t_buf + (uint32_t)(cp * 64 + 8 * (t & 3)), bd, idesc_pv, 1u);
               }
               stamp(k, 1 + cp);
               if (cp == 3) {
@@ -511,7 +520,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         if (progress) {
           t_idle = clock64();
         } else if (clock64() - t_idle > 4000000000LL) {
-          printf("attention_tc2: issuer stalled (block %d, S items %d/%d, PV items %d/%d chunks %d/%d, done %d of %d)\n",
+          printf("attention_tc3: issuer stalled (block %d, S items %d/%d, PV items %d/%d chunks %d/%d, done %d of %d)\n",
                  (int)blockIdx.x, s_k[0], s_k[1], p_k[0], p_k[1], p_cp[0], p_cp[1], done, nitems);
           __trap();
         }
@@ -525,8 +534,19 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
     const bool tr = tracing && quarter == 0 && lane == 0;
+    const int b = grp;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
+    uint32_t zeros[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) zeros[i] = 0u;
+    if (ZERO_S && grp < nitems) {  // this warp's lanes of the whole buffer, before its first S accumulates into them
+#pragma unroll
+      for (int c = 0; c < 8; ++c) tmem_st32(taddr + 32 * c, zeros);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_b(FREE, b));
+    }
     for (int k = grp; k < nitems; k += 2) {
-      const int b = grp;
       const uint32_t ph = (uint32_t)(k >> 1) & 1u;
       const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
       const int ncols = (it.kv_rows + 15) & ~15;
@@ -542,17 +562,32 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
       const int wlo = __reduce_min_sync(0xffffffffu, lo);
       const int whi = __reduce_max_sync(0xffffffffu, hi);
       const bool uniform = (g == 0);  // split mode: every row of the tile has the same key range
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
       if (tr) stamp(k, 5);
       mbar_wait(bar_b(S_FULL, b), ph, 30);
       fence_after();
       if (tr) stamp(k, 6);
-      float m_run = -INFINITY;
-      float mc[4], lc[4];
+      // ---- pass 1: the row maximum over the whole score row ----
+      float m_row = -INFINITY;
 #pragma unroll
       for (int cp = 0; cp < 4; ++cp) {
-        mc[cp] = -INFINITY;
-        lc[cp] = 0.f;
+        const int c0 = cp * 64;
+        if (cp < npair && !(c0 + 64 <= wlo || c0 >= whi)) {
+          float v[64];
+          tmem_ld64(taddr + c0, v);
+          if (!(uniform && c0 + 64 <= hi)) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
+          }
+          m_row = fmaxf(m_row, at_max64(v));
+        }
+      }
+      const float msc = m_row * sl2;  // every row has at least one key of its own
+      if (tr) stamp(k, 7);
+      // ---- pass 2: P_c = 2^(s * sl2 - msc) per 64-key chunk, bf16 pairs back into the chunk's own columns ----
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
         if (cp < npair) {
           const int c0 = cp * 64;
           uint32_t pk[32];
@@ -567,9 +602,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
               for (int i = 0; i < 64; ++i)
                 if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
             }
-            const float m_new = fmaxf(m_run, at_max64(v) * sl2);
-            const float msc = (m_new == -INFINITY) ? 0.f : m_new;  // row has no key yet (packed mode)
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {  // FFMA2 for the scale/shift, MUFU.EX2, FADD2 for the row sum
               fma_f32x2(v[i], v[i + 1], sl2, -msc);
@@ -583,43 +615,31 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
               pk[i >> 1] = cvt_bf16x2(v[i], v[i + 1]);          // column j of P_c = keys (2j, 2j+1)
               pk[(i >> 1) + 1] = cvt_bf16x2(v[i + 2], v[i + 3]);
             }
-            mc[cp] = m_new;
-            lc[cp] = (s0 + s1) + (s2 + s3);
-            m_run = m_new;
           }
-          // P_c over the first half of the chunk's own (already read) score columns; O_c will take the second half
-          tmem_st32(taddr + c0, pk);
+          tmem_st32(taddr + c0, pk);                    // P_c over the first half of the chunk's own score columns
+          if (cp == 0) tmem_st32(taddr + 32, zeros);    // O = 0 in the (consumed) second half of chunk 0
           fence_before();
         }
         // (chunks past the item's keys are signalled too: the barrier phases must advance once per item)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p(b, cp));
-        if (tr) stamp(k, 7 + cp);
+        if (tr) stamp(k, 8 + (cp < 3 ? cp : 2));
       }
-      // ---- epilogue: O = sum_c 2^(m_c - m) O_c, row sum likewise, O / rowsum -> bf16 ----
-      float fc[4], sum = 0.f;
-#pragma unroll
-      for (int cp = 0; cp < 4; ++cp) {
-        fc[cp] = (mc[cp] == -INFINITY) ? 0.f : at_ex2(mc[cp] - m_run);
-        sum += fc[cp] * lc[cp];
-      }
+      const float sum = (s0 + s1) + (s2 + s3);
+      // ---- epilogue: O / rowsum -> bf16 ----
       mbar_wait(bar_b(O_FULL, b), ph, 31);
       fence_after();
       if (tr) stamp(k, 11);
       {
         float o[32];
+        tmem_ld32(taddr + 32, o);
+        if (ZERO_S) {  // score columns back to zero for the buffer's next Q K^T (this warp's lanes only)
+          const int nz = (ncols + 31) >> 5;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int cp = 0; cp < 4; ++cp) {
-          if (cp < npair) {
-            float oc[32];
-            tmem_ld32(taddr + cp * 64 + 32, oc);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = fmaf(fc[cp], oc[i], o[i]);
-          }
+          for (int c = 0; c < 8; ++c)
+            if (c < nz) tmem_st32(taddr + 32 * c, zeros);
         }
-        fence_before();  // O_c reads precede the next S overwriting the buffer
+        fence_before();  // O read (and the zero-fill) precede the next S
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_b(FREE, b));  // release TMEM before the global stores
         const float inv = 1.0f / sum;
@@ -700,13 +720,15 @@ static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
   return 0;
 }
 
-// CSE_ATTN_V2=0 keeps the v1 kernel (two issuer warps, P through shared memory) for A/B runs.
-static bool attention_v2_enabled() {
-  static const bool on = []() {
-    const char* e = getenv("CSE_ATTN_V2");
-    return e == nullptr || e[0] != '0';
+// CSE_ATTN_VER = 1 keeps the v1 kernel (two issuer warps, P through shared memory, one accumulator per chunk),
+// 3 = v3, 4 = v3 with zero-filled score columns (default; see the v3 header) — for A/B runs.
+static int attention_version() {
+  static const int ver = []() {
+    const char* e = getenv("CSE_ATTN_VER");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return (v == 1 || v == 3 || v == 4) ? v : 4;
   }();
-  return on;
+  return ver;
 }
 
 long long* g_attention_trace = nullptr;  // cse_debug_attention_trace: device buffer [64 items][16 slots] of clock64 stamps
@@ -716,13 +738,17 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     set_error("attention_tc: n=%d outside [1,256]", n);
     return 1;
   }
-  const bool v2 = g_attention_mode == 3 || (g_attention_mode != 2 && attention_v2_enabled());
+  // cse_debug_force_mma_attention: 2 = v1, 3 = v3, 4 = v3 + zero-filled scores; otherwise CSE_ATTN_VER
+  const int ver = g_attention_mode == 2 ? 1 : (g_attention_mode == 3 || g_attention_mode == 4) ? g_attention_mode
+                                                                                                : attention_version();
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAtSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
+      e = cudaFuncSetAttribute(attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return 1;
@@ -740,10 +766,15 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     return 1;
   }
   const int grid = (int)(items < sms ? items : sms);
-  if (v2) {
-    launch_pdl(attention_tc2_kernel, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g, (int)items,
-               g_attention_trace);
-    return check_launch("attention_tc2_kernel");
+  if (ver == 4) {
+    launch_pdl(attention_tc3_kernel<true>, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g,
+               (int)items, g_attention_trace);
+    return check_launch("attention_tc3_kernel<1>");
+  }
+  if (ver == 3) {
+    launch_pdl(attention_tc3_kernel<false>, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g,
+               (int)items, g_attention_trace);
+    return check_launch("attention_tc3_kernel<0>");
   }
   launch_pdl(attention_tc_kernel, dim3(grid), dim3(kAtThreads), kAtSmem, st, 1, tm, out, n, nseq, g, (int)items);
   return check_launch("attention_tc_kernel");

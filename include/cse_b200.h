@@ -439,6 +439,34 @@ CSE_API int cse_layer_bwd_bf16(const cse_layer_params* p_host, const cse_layer_g
                                const float* R_in, float* dR, int nseq, int n,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fused optimiser step ----
+ * Replaces, per update (train_ContSep.py:233,402-419; train_ContExt.py:372-389):
+ *   scaler.unscale_(optimizer); grad_norm = clip_grad_norm_(model.parameters(), max_norm=5.0);
+ *   [skip when the norm is not finite] optimizer.step() with optim.AdamW(amsgrad=True); scaler.update()
+ * by three launches over a table of <= 16384-element chunks of the parameter tensors, without the reference's host
+ * synchronisation on the norm.
+ *   cse_optim_chunk_count   chunks a parameter list needs (host arithmetic; -1 on bad input)
+ *   cse_optim_table_fill    writes the 48-byte chunk descriptors {param, grad, exp_avg, exp_avg_sq,
+ *                           max_exp_avg_sq, n, pad} for DEVICE pointers into a caller-owned HOST buffer, which
+ *                           the caller copies to the device (max_exp_avg_sq may be NULL when amsgrad == 0)
+ *   cse_optim_step          device_table: that copy; state: 64 B of zero-initialised device memory
+ *                           {double step; float scale; int growth_tracker; float total_norm; float coef;
+ *                            int found_inf; float step_size; float bc2_sqrt; float reserved[7]} (set `scale`
+ *                           to the GradScaler's initial scale when use_scaler != 0); partial: n_chunks floats
+ *                           of device scratch.  total_norm is the norm of the unscaled gradients
+ *                           (clip_grad_norm_'s return value); found_inf = 1 means the update was skipped and,
+ *                           with use_scaler, the scale backed off — GradScaler.step/update semantics.
+ *                           write_back_grads != 0 also stores the unscaled, clipped gradients (what
+ *                           clip_grad_norm_ leaves in .grad). */
+CSE_API long long cse_optim_chunk_count(int n_tensors, const long long* numel);
+CSE_API int cse_optim_table_fill(int n_tensors, const long long* numel, void* const* param, void* const* grad,
+                                 void* const* exp_avg, void* const* exp_avg_sq, void* const* max_exp_avg_sq,
+                                 void* host_table, size_t host_table_bytes);
+CSE_API int cse_optim_step(const void* device_table, long long n_chunks, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int amsgrad, float max_norm, int use_scaler,
+                           float growth_factor, float backoff_factor, int growth_interval, int write_back_grads,
+                           void* state, float* partial, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

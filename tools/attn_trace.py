@@ -1,10 +1,10 @@
-"""Attention kernel A/B timing + pipeline trace of the tcgen05 v2 kernel (debug tool, not a product path).
+"""Attention kernel A/B timing + pipeline trace of the tcgen05 v3 kernel (debug tool, not a product path).
 
     python tools/attn_trace.py            # on the GPU box
 
 1. CUDA-event timing (20 launches after 3 warm-ups, inputs larger than L2 for the big shapes) of every bf16
-   attention kernel at the shapes of BASELINE configs[1] / [3]:  mma.sync | tcgen05 v1 | tcgen05 v2.
-2. clock64 trace of CTA 0 of the v2 kernel (cse_debug_attention_trace) at the intra shape: per item, cycles relative
+   attention kernel at the shapes of BASELINE configs[1] / [3]:  mma.sync | tcgen05 v1 | tcgen05 v3 | v3 with zero-filled score columns.
+2. clock64 trace of CTA 0 of the v3 kernel (cse_debug_attention_trace) at the intra shape: per item, cycles relative
    to the item's S issue, so the dead time between the MUFU and tensor phases is visible.
 """
 import ctypes as C
@@ -19,9 +19,10 @@ import cse_b200  # noqa: E402,F401
 from cse_b200 import _lib  # noqa: E402
 
 DEV = "cuda:0"
+TRACE_MODE = int(os.environ.get("ATTN_TRACE_MODE", "4"))
 BF16 = _lib.BF16
-SLOTS = ["S issue", "PV0 issue", "PV1", "PV2", "PV3", "sm wait S", "sm S seen", "sm c0 done", "sm c1 done", "sm c2 done",
-         "sm c3 done", "sm O seen", "sm epi done", "QK load issue", "V load issue", "-"]
+SLOTS = ["S issue", "PV0 issue", "PV1", "PV2", "PV3", "sm wait S", "sm S seen", "sm max done", "sm c0 done", "sm c1 done",
+         "sm c2/3 done", "sm O seen", "sm epi done", "QK load issue", "V load issue", "-"]
 
 
 def run(qkv, nseq, n, out, mode):
@@ -51,11 +52,12 @@ def timeit(nseq, n, mode, iters=20):
 
 
 def main():
-    names = {1: "mma.sync", 2: "tcgen05 v1", 3: "tcgen05 v2"}
-    print("shape (nseq x n)          " + "".join(f"{names[m]:>14}" for m in (1, 2, 3)) + "   [us per launch]")
+    names = {1: "mma.sync", 2: "tcgen05 v1", 3: "tcgen05 v3", 4: "v3 + zero S"}
+    modes = (1, 2, 3, 4)
+    print("shape (nseq x n)          " + "".join(f"{names[m]:>14}" for m in modes) + "   [us per launch]")
     for nseq, n in [(544, 251), (4000, 35), (1040, 252), (2000, 132), (4000, 67), (4000, 19)]:
         row, outs = [], {}
-        for m in (1, 2, 3):
+        for m in modes:
             try:
                 us, outs[m] = timeit(nseq, n, m)
                 row.append(f"{us:14.1f}")
@@ -63,27 +65,28 @@ def main():
                 row.append(f"{'ERR':>14}")
                 print("   ", type(e).__name__, str(e)[:200])
         agree = ""
-        if 1 in outs and 3 in outs:
-            d = (outs[3].float() - outs[1].float()).norm() / outs[1].float().norm()
-            agree = f"   v2 vs mma rel-L2 {d.item():.2e}"
+        for m in (3, 4):
+            if 1 in outs and m in outs:
+                d = (outs[m].float() - outs[1].float()).norm() / outs[1].float().norm()
+                agree += f"   mode {m} vs mma rel-L2 {d.item():.2e}"
         print(f"{nseq:6d} x {n:3d}             " + "".join(row) + agree)
 
-    # ---- trace of CTA 0, v2, intra shape ----
+    # ---- trace of CTA 0, v3 (+ zero-filled scores), intra shape ----
     nseq, n = 544, 251
     g = torch.Generator(device=DEV).manual_seed(1)
     qkv = (torch.randn(nseq * n, 768, device=DEV, generator=g) * 1.5).to(torch.bfloat16)
     out = torch.empty(nseq * n, 256, dtype=torch.bfloat16, device=DEV)
     buf = torch.zeros(64 * 16, dtype=torch.int64, device=DEV)
     lib = _lib.load()
-    run(qkv, nseq, n, out, 3)
+    run(qkv, nseq, n, out, TRACE_MODE)
     torch.cuda.synchronize()
     lib.cse_debug_attention_trace(C.c_void_p(buf.data_ptr()))
-    run(qkv, nseq, n, out, 3)
+    run(qkv, nseq, n, out, TRACE_MODE)
     torch.cuda.synchronize()
     lib.cse_debug_attention_trace(None)
     t = buf.cpu().view(64, 16)
     t0 = int(t[0][t[0] > 0].min())
-    print("\nv2 trace, CTA 0, intra shape 544 x 251: cycles since the CTA's first event; one line per item "
+    print(f"\nmode {TRACE_MODE} trace, CTA 0, intra shape 544 x 251: cycles since the CTA's first event; one line per item "
           "(even items = softmax group 0, odd = group 1)")
     print("item  " + "".join(f"{s:>14}" for s in SLOTS[:15]))
     for k in range(64):

@@ -1,8 +1,7 @@
 // Development microbenchmark (not part of the product): tensor-pipe cost of the tcgen05.mma shapes the attention
 // kernel issues — M = 128, K = 16, bf16 — as a function of N, the B operand's major-ness / swizzle (V is consumed
 // MN-major exactly as TMA wrote it), the A operand's home (shared memory / tensor memory), and the issue pattern:
-//   chain : every instruction accumulates into ONE accumulator (a dependent chain)
-//   quad  : groups of 4 instructions per accumulator (first overwrites), accumulators rotate over `nacc` column groups
+// and of how often an instruction OVERWRITES the accumulator (scale-d = 0) instead of accumulating into it.
 // nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/micro/umma_pv_rate tools/micro/umma_pv_rate.cu
 #include <cstdint>
 #include <cstdio>
@@ -19,7 +18,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo, 
 }
 
 struct Cfg {
-  int N, ts, b_mn, sw64, quad, nacc;
+  int N, ts, b_mn, sw64, fresh_every, zero_st;
 };
 
 __global__ void __launch_bounds__(128, 1) k(Cfg c, int iters, long long* cyc) {
@@ -50,11 +49,11 @@ __global__ void __launch_bounds__(128, 1) k(Cfg c, int iters, long long* cyc) {
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const int j = i & 3;
-      const uint32_t acc = c.quad ? (j != 0) : 1u;
-      const uint32_t d = tb + 256 + (c.quad ? (uint32_t)((i >> 2) % c.nacc) * 64u : 0u) + (c.ts && c.quad ? 32u : 0u);
+      const uint32_t acc = (c.fresh_every > 0 && i % c.fresh_every == 0) ? 0u : 1u;
+      const uint32_t d = tb + 256;
       const uint64_t bd = bd0 + (uint64_t)(bstep * j);
       if (c.ts) {
-        const uint32_t a = c.quad ? (d - 32u + 8u * j) : tb;  // as the attention kernel: P_c beside its O_c
+        const uint32_t a = tb + 8u * j;
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a), "l"(bd), "r"(idesc), "r"(acc) : "memory");
       } else {
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(ad + 2 * j), "l"(bd), "r"(idesc), "r"(acc) : "memory");
@@ -74,28 +73,24 @@ int main() {
   long long* cyc;
   cudaMalloc(&cyc, 148 * 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int iters = 4000;
-  printf("cycles per tcgen05.mma (M=128, K=16, bf16)\n");
-  printf("%4s %5s %6s %5s %6s %5s %8s\n", "N", "A", "Bmajor", "swz", "issue", "nacc", "cycles");
-  for (int quad = 0; quad < 2; ++quad)
-    for (int ts = 0; ts < 2; ++ts)
-      for (int b_mn = 0; b_mn < 2; ++b_mn)
-        for (int sw64 = 0; sw64 < 2; ++sw64)
-          for (int N : {32, 64, 128, 256}) {
-            if (b_mn && sw64 && N > 32) continue;   // a 64-B swizzle row holds 32 MN elements
-            if (b_mn && !sw64 && N > 64) continue;  // a 128-B swizzle row holds 64 MN elements
-            if (!b_mn && sw64) continue;            // K-major B: SWIZZLE_128B only
-            if (quad && N > 64) continue;
-            for (int nacc : {1, 4}) {
-              if (!quad && nacc > 1) continue;
-              Cfg c{N, ts, b_mn, sw64, quad, nacc};
-              k<<<148, 128, 100 * 1024>>>(c, iters, cyc);
-              cudaError_t e = cudaDeviceSynchronize();
-              long long h;
-              cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
-              printf("%4d %5s %6s %5s %6s %5d %8.1f   %s\n", N, ts ? "TMEM" : "smem", b_mn ? "MN" : "K", sw64 ? "64B" : "128B",
-                     quad ? "quad" : "chain", nacc, (double)h / iters, e == cudaSuccess ? "" : cudaGetErrorString(e));
-            }
-          }
+  const int iters = 4096;
+  printf("cycles per tcgen05.mma (M=128, K=16, bf16); fresh_every = k: every k-th instruction overwrites the accumulator (scale-d = 0)\n");
+  printf("%4s %5s %6s %5s %12s %8s\n", "N", "A", "Bmajor", "swz", "fresh_every", "cycles");
+  for (int ts = 0; ts < 2; ++ts)
+    for (int b_mn = 0; b_mn < 2; ++b_mn)
+      for (int N : {32, 64, 128, 256}) {
+        if (b_mn && N != 32) continue;
+        const int sw64 = b_mn;  // the attention kernel's V operand: MN-major, SWIZZLE_64B, N = 32
+        for (int fe : {0, 1, 2, 4, 16}) {
+          Cfg c{N, ts, b_mn, sw64, fe, 0};
+          k<<<148, 128, 100 * 1024>>>(c, iters, cyc);
+          cudaError_t e = cudaDeviceSynchronize();
+          long long h;
+          cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+          printf("%4d %5s %6s %5s %12d %8.1f   %s\n", N, ts ? "TMEM" : "smem", b_mn ? "MN" : "K", sw64 ? "64B" : "128B", fe,
+                 (double)h / iters, e == cudaSuccess ? "" : cudaGetErrorString(e));
+          if (e != cudaSuccess) return 1;
+        }
+      }
   return 0;
 }
