@@ -116,6 +116,9 @@ _SIGNATURES = {
     "cse_layer_bwd_bf16_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cse_layer_bwd_bf16": (C.c_int, [C.POINTER(LayerParams), C.POINTER(LayerGrads), _v, _v, C.c_int, C.c_int, _v,
                                      C.c_size_t, _v]),
+    "cse_sdr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "cse_sdr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _v, _v, C.c_size_t, _v]),
+    "cse_metric_update": (C.c_int, [_v, C.c_int, _v, _v]),
     "cse_optim_chunk_count": (C.c_longlong, [C.c_int, C.POINTER(C.c_longlong)]),
     "cse_optim_table_fill": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)] + [C.POINTER(_v)] * 5 + [_v, C.c_size_t]),
     "cse_optim_step": (C.c_int, [_v, C.c_longlong] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, C.c_float,

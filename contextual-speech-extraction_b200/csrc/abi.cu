@@ -347,12 +347,12 @@ const char* cse_last_error(void) { return g_err; }
 long long cse_launch_count(void) { return g_launches.load(); }
 
 int cse_debug_force_mma_attention(int on) {
-  g_attention_mode = on;  // 0 auto, 1 force mma.sync, 2 force tcgen05 v1 (n <= 256), 3 force tcgen05 v3, 4 force v3 with zero-filled score columns
+  g_attention_mode = on;  // 0 auto, 1 force mma.sync, 2 force tcgen05 v1 (n <= 256), 4 force tcgen05 v4
   return 0;
 }
 
 int cse_debug_attention_trace(long long* device_buffer) {
-  g_attention_trace = device_buffer;  // [64 items][16 slots] of clock64 stamps written by CTA 0 of attention_tc3_kernel; NULL = off
+  g_attention_trace = device_buffer;  // [64 items][16 slots] of clock64 stamps written by CTA 0 of attention_tc4_kernel; NULL = off
   return 0;
 }
 

@@ -336,44 +336,83 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// v3.  What bounded v1 (and a first re-plumbing, "v2", that kept its arithmetic) was not MUFU and not the issue
-// order but the tensor pipe itself: a tcgen05.mma that OVERWRITES its accumulator (scale-d = 0) costs ~775 cycles
-// at M = 128 whatever N is, against ~105 for one that accumulates (tools/micro/umma_pv_rate.cu, B200: groups of
-// "1 overwrite + 3 accumulate" average 273 cycles per instruction, pure accumulate chains 105).  The online softmax
-// gave every 64-key chunk its own O_c accumulator, i.e. 4 overwriting instructions + 1 for S per item: ~4.4 k of
-// the ~4.8 k cycles an item took.  v3 therefore
-//   * takes the row maximum over the WHOLE score row first (a second tcgen05.ld pass over S is ~150 cycles per
-//     item), so every P_c is exponentiated against the final maximum and all sixteen P_c V_c instructions
-//     ACCUMULATE into one O tile that the softmax warps zero-fill with tcgen05.st;
-//   * (ZERO_S) lets the softmax warps zero-fill the score columns as well, so that Q K^T accumulates too;
-//   * keeps v2's plumbing: ONE issuing warp polls (mbarrier.test_wait) every pending piece of tensor work of both
-//     in-flight items and issues whichever is ready, S of the next item first; P never touches shared memory (bf16
-//     pairs go back into the item's own consumed score columns and feed P_c V_c as the TMEM A operand), and the
-//     128 KB of P staging v1 needed are a 4-deep Q/K/V ring.
+// v4.  What bounded v1 (148 us at 544 x 251, ~4.8 k cycles per item) was neither MUFU nor the tensor pipe but the
+// INSTRUCTION STREAM OF THE ISSUING THREADS: tools/micro/umma_pv_rate.cu issues one item's eighteen tcgen05.mma from a
+// fully unrolled body in ~850 cycles (45-55 per instruction, whatever the accumulator pattern, P in shared or tensor
+// memory, with the softmax warps' tcgen05.ld/st traffic beside it), while the kernels' issue loops — item decode,
+// descriptor construction, barrier address arithmetic, R2UR moves, ~100 dependent instructions per 4-instruction
+// chunk — took ~1000 cycles per chunk (clock64 traces, profiles/r02_attention_trace.txt).  v4 therefore has
+//   * one issuing thread PER TMEM BUFFER (warps 1 and 10), each strictly sequential (S_k, P V_k chunks 0-3,
+//     S_{k+2}, ...): no polling, descriptors are a precomputed low word + constant, the four instructions of a
+//     chunk are unrolled;
+//   * a softmax warp's time is dominated by TMEM round trips (~250-300 cycles per tcgen05.ld / tcgen05.st + wait;
+//     a two-pass variant with the row maximum taken first measured 2.4 k cycles for that pass alone), so the
+//     single-pass online softmax stays (per-chunk maxima m_c and accumulators O_c, re-weighted by 2^(m_c - m)
+//     in the epilogue), with the score load of chunk c+1 in flight while chunk c is exponentiated, the
+//     tcgen05.st of P_c completing under the maximum search of chunk c+1, and the four O_c loads of the
+//     epilogue issued together;
+//   * P never touches shared memory: bf16 pairs go back into the item's own consumed score columns and feed
+//     P_c V_c as the TMEM A operand; the 128 KB of P staging of v1 are a 4-deep Q/K/V ring;
+//   * POLY pairs out of every 8 pairs of exponentials can be evaluated on the FMA pipe (Cody-Waite split + degree-3
+//     polynomial, relative error 7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2; measured no gain
+//     (174 / 170 / 172 us at POLY = 0 / 2 / 3) while the kernel is not MUFU-bound, so only POLY = 0 is instantiated.
 // TMEM columns of buffer b (256 per item): chunk c (64 keys) = [64c, 64c+64): scores -> P_c in [64c, 64c+32)
-// (two bf16 per column); O (fp32 [128 x 32]) in [32, 64), the dead upper half of chunk 0.
+// (two bf16 per column), O_c (fp32 [128 x 32]) in [64c+32, 64c+64).
 // ------------------------------------------------------------------------------------------
-constexpr int kA2Threads = 320;  // warp 0 TMA, warp 1 S/PV issuer, warps 2-5 softmax group 0, warps 6-9 group 1
+// warp 0 TMA, warps 1 / 2 issuers of TMEM buffer 0 / 1, warps 3-18 softmax: group (= buffer) x key half x lane quarter
+constexpr int kA4Threads = 608;
+constexpr long long kA4Stagger = 3500;  // cycles: about half of one group's item period
+constexpr int kA4Regs = 96;   // five warps on one SM sub-partition (16 K registers each): 5 x 32 x 96 = 15360
 constexpr int kA2Stages = 4;
 constexpr int kA2StageBytes = kAtQ + 2 * kAtKV;  // 40 KB: Q tile + K + V
-constexpr size_t kA2Smem = 1024 + (size_t)kA2Stages * kA2StageBytes + 512;
+constexpr size_t kA2Smem = 1024 + (size_t)kA2Stages * kA2StageBytes + 512 + 2 * 2 * 2 * 128 * 16;
 constexpr int kA2TraceSlots = 16, kA2TraceItems = 64;
 
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for x <= 0 on the FMA pipe: x = j + f, j = round(x), |f| <= 0.5; 2^f by a degree-3 minimax polynomial
+// (max relative error 7.5e-5), 2^j by adding j to the exponent field.  Inputs below -126 (masked keys: -inf)
+// are clamped; they come out as ~1e-38 instead of 0.
+__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to an integer in the low mantissa bits
+  x0 = fmaxf(x0, -126.f);  // (-127 would wrap the exponent field)
+  x1 = fmaxf(x1, -126.f);
+  const unsigned long long x = pack_f32x2(x0, x1);
+  const unsigned long long xf = fadd2(x, pack_f32x2(kMagic, kMagic));
+  const unsigned long long j = fadd2(xf, pack_f32x2(-kMagic, -kMagic));
+  const unsigned long long f = ffma2(j, pack_f32x2(-1.f, -1.f), x);
+  unsigned long long pq = ffma2(pack_f32x2(0.055170804f, 0.055170804f), f, pack_f32x2(0.24260928f, 0.24260928f));
+  pq = ffma2(pq, f, pack_f32x2(0.69326097f, 0.69326097f));
+  pq = ffma2(pq, f, pack_f32x2(0.99992818f, 0.99992818f));
+  float p0, p1, f0, f1;
+  unpack_f32x2(pq, p0, p1);
+  unpack_f32x2(xf, f0, f1);
+  x0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(f0) << 23));
+  x1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(f1) << 23));
 }
 
-template <bool ZERO_S>
-__global__ void __launch_bounds__(kA2Threads, 1)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
+__device__ __forceinline__ float at_max32(const uint32_t (&u)[32]) {
+  float m0 = __uint_as_float(u[0]), m1 = __uint_as_float(u[1]);
+#pragma unroll
+  for (int i = 2; i < 30; i += 4) {
+    m0 = max3_f32(m0, __uint_as_float(u[i]), __uint_as_float(u[i + 2]));
+    m1 = max3_f32(m1, __uint_as_float(u[i + 1]), __uint_as_float(u[i + 3]));
+  }
+  return fmaxf(max3_f32(m0, m1, __uint_as_float(u[30])), __uint_as_float(u[31]));
+}
+
+template <int POLY>
+__global__ void __maxnreg__(kA4Regs)
+attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int n, int nseq,
                      int g, int items, long long* __restrict__ trace) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -398,6 +437,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
   auto stamp = [&](int k, int slot) {
     if (tracing && k < kA2TraceItems) trace[k * kA2TraceSlots + slot] = clock64();
   };
+  // Every item has the same key count except, in packed mode, the items of the last (partial) unit.
+  const int units = g > 0 ? (nseq + g - 1) / g : 2 * nseq;
+  const int kv_full = g > 0 ? g * n : n, kv_last = g > 0 ? (nseq - (units - 1) * g) * n : n;
+  auto item_index = [&](int k) { return items - 1 - ((int)blockIdx.x + k * (int)gridDim.x); };  // descending sweep
+  auto item_ncols = [&](int k) { return (((item_index(k) >> 3) == units - 1 ? kv_last : kv_full) + 15) & ~15; };
 
   if (threadIdx.x == 0) {
     for (int st = 0; st < kA2Stages; ++st) {
@@ -409,8 +453,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_b(S_FULL, b), 1);
       mbar_init(bar_b(O_FULL, b), 1);
-      mbar_init(bar_b(FREE, b), 4);
-      for (int cp = 0; cp < 4; ++cp) mbar_init(bar_p(b, cp), 4);  // one arrive per softmax warp of the group
+      mbar_init(bar_b(FREE, b), 8);                                // the group's eight softmax warps
+      for (int cp = 0; cp < 4; ++cp) mbar_init(bar_p(b, cp), 4);  // the four lane quarters of the chunk's key half
     }
     mbar_fence_init();
   }
@@ -428,7 +472,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
       for (int k = 0; k < nitems; ++k) {
         const int st = k & (kA2Stages - 1);
         const uint32_t ph = (uint32_t)(k / kA2Stages) & 1u;
-        const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
+        const AtItem it = at_decode(item_index(k), n, nseq, g);
         const int nk = it.kv_rows > 128 ? 2 : 1;
         if (lane == 0) {
           if (k >= kA2Stages) mbar_wait(bar_st(QK_EMPTY, st), ph ^ 1u, 10);  // S of item k-4 has consumed the stage
@@ -447,211 +491,258 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================= the one tensor-pipe issuer: S = Q K^T and O += P_c V_c of both in-flight items ==========
+  } else if (warp == 1 || warp == 2) {
+    // ================= tensor-pipe issuer of TMEM buffer b: S_k, P V_k chunk 0..3, S_{k+2}, ... =================
     if (lane == 0) {
+      const int b = warp - 1;
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1);  // A = P from TMEM, B = V MN-major
-      int s_k[2] = {0, 1};   // next item (CTA-local index) whose S goes to TMEM buffer b
-      int p_k[2] = {0, 1};   // item whose PV chunks are being issued on buffer b
-      int p_cp[2] = {0, 0};  // its next chunk
-      int done = 0;
-      long long t_idle = clock64();
-      while (done < nitems) {
-        bool progress = false;
+      // descriptor words (tc::make_desc): low = start >> 4 | LBO field 1; high = SBO >> 4 | version | layout
+      constexpr uint32_t kDescHi64 = (512u >> 4) | (1u << 14) | (kLayoutSw64 << 29);
+      constexpr uint32_t kStep = (uint32_t)kA2StageBytes >> 4;
+      const uint32_t q_lo0 = ((sQ(0) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t k_lo0 = ((sK(0) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t v_lo0 = ((sV(0) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t t_buf = tmem_base + (uint32_t)b * 256;
+      const uint32_t bS = bar_b(S_FULL, b), bO = bar_b(O_FULL, b), bF = bar_b(FREE, b), bP = bar_p(b, 0);
+      for (int k = b; k < nitems; k += 2) {
+        const uint32_t st = (uint32_t)k & (kA2Stages - 1);
+        const uint32_t ph_st = ((uint32_t)k / kA2Stages) & 1u, ph_b = ((uint32_t)k >> 1) & 1u;
+        const int ncols = item_ncols(k);
+        const int ksteps = ncols >> 4;
+        // ---- S = Q K^T ----
+        mbar_wait_spin(bar_st(QK_FULL, st), ph_st, 22);
+        if (k >= 2) mbar_wait_spin(bF, ph_b ^ 1u, 23);  // O of item k-2 has been read out of this buffer
+        fence_after();
+        {
+          const uint32_t idesc_s = make_idesc_bf16(128, ncols, 0, 0);
+          const uint64_t qd = desc_from(q_lo0 + st * kStep, kDescHi64), kd = desc_from(k_lo0 + st * kStep, kDescHi64);
+          umma_bf16(t_buf, qd, kd, idesc_s, 0u);
+          umma_bf16(t_buf, qd + 2, kd + 2, idesc_s, 1u);  // second k16 step: +32 B inside the 64-B row
+          umma_commit(bS);
+          umma_commit(bar_st(QK_EMPTY, st));
+        }
+        stamp(k, 0);
+        // ---- O_c = P_c V_c, c = 0..3 ----
+        mbar_wait_spin(bar_st(V_FULL, st), ph_st, 21);
+        const uint64_t vd = desc_from(v_lo0 + st * kStep, kDescHi64);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          // ---- S of the next item of this buffer (first: it unblocks a whole softmax group) ----
-          int k = s_k[b];
-          if (k < nitems) {
-            const int st = k & (kA2Stages - 1);
-            const uint32_t ph_st = (uint32_t)(k / kA2Stages) & 1u, ph_b = (uint32_t)(k >> 1) & 1u;
-            // FREE completes once per item (its O has been read out) — and, with ZERO_S, once more at kernel start
-            // (the group's first zero-fill), so use j of the buffer waits for completion j instead of j - 1
-            const bool buf_free = ZERO_S ? mbar_test(bar_b(FREE, b), ph_b) : (k < 2 || mbar_test(bar_b(FREE, b), ph_b ^ 1u));
-            if (buf_free && mbar_test(bar_st(QK_FULL, st), ph_st)) {
-              fence_after();
-              const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
-              const int ncols = (it.kv_rows + 15) & ~15;
-              const uint32_t idesc_s = make_idesc_bf16(128, ncols, 0, 0);
-              const uint64_t ad = make_desc(sQ(st), 512, kLayoutSw64);
-              const uint64_t bd = make_desc(sK(st), 512, kLayoutSw64);
-              const uint32_t d_s = tmem_base + (uint32_t)b * 256;
-              umma_bf16(d_s, ad, bd, idesc_s, ZERO_S ? 1u : 0u);
-              umma_bf16(d_s, ad + 2, bd + 2, idesc_s, 1u);  // second k16 step: +32 B inside the 64-B row
-              umma_commit(bar_b(S_FULL, b));
-              umma_commit(bar_st(QK_EMPTY, st));
-              stamp(k, 0);
-              s_k[b] = k + 2;
-              progress = true;
-            }
+        for (int cp = 0; cp < 4; ++cp) {
+          mbar_wait_spin(bP + 8 * cp, ph_b, 24);
+          fence_after();
+          const uint32_t a0 = t_buf + (uint32_t)cp * 64;
+          const uint64_t vc = vd + (uint64_t)(cp * 4 * 64);   // 1024 B of V per 16 keys
+          const int left = ksteps - 4 * cp;
+          if (left >= 4) {
+            umma_bf16_ts(a0 + 32, a0, vc, idesc_pv, 0u);
+            umma_bf16_ts(a0 + 32, a0 + 8, vc + 64, idesc_pv, 1u);
+            umma_bf16_ts(a0 + 32, a0 + 16, vc + 128, idesc_pv, 1u);
+            umma_bf16_ts(a0 + 32, a0 + 24, vc + 192, idesc_pv, 1u);
+          } else {
+            for (int j = 0; j < left; ++j)
+              umma_bf16_ts(a0 + 32, a0 + 8 * (uint32_t)j, vc + (uint64_t)(64 * j), idesc_pv, j != 0 ? 1u : 0u);
           }
-          // ---- next P_c V_c chunk of the item in flight on this buffer ----
-          k = p_k[b];
-          if (k < nitems && k < s_k[b]) {
-            const int st = k & (kA2Stages - 1);
-            const uint32_t ph_st = (uint32_t)(k / kA2Stages) & 1u, ph_b = (uint32_t)(k >> 1) & 1u;
-            const int cp = p_cp[b];
-            if ((cp > 0 || mbar_test(bar_st(V_FULL, st), ph_st)) && mbar_test(bar_p(b, cp), ph_b)) {
-              fence_after();
-              const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
-              const int ncols = (it.kv_rows + 15) & ~15;
-              const int npair = (ncols + 63) >> 6;
-              const uint32_t t_buf = tmem_base + (uint32_t)b * 256;
-              const int t1 = (cp < npair) ? min(4 * cp + 4, ncols / 16) : 0;
-              for (int t = 4 * cp; t < t1; ++t) {
-                const uint64_t bd = make_desc(sV(st) + (uint32_t)t * 1024, 512, kLayoutSw64);
-                // every instruction accumulates: the softmax warps zero-filled O before signalling chunk 0
-                umma_bf16_ts(t_buf + 32, t_buf + (uint32_t)(cp * 64 + 8 * (t & 3)), bd, idesc_pv, 1u);
-              }
-              stamp(k, 1 + cp);
-              if (cp == 3) {
-                umma_commit(bar_b(O_FULL, b));
-                umma_commit(bar_st(V_EMPTY, st));
-                p_k[b] = k + 2;
-                p_cp[b] = 0;
-                ++done;
-              } else {
-                p_cp[b] = cp + 1;
-              }
-              progress = true;
-            }
-          }
+          stamp(k, 1 + cp);
         }
-        if (progress) {
-          t_idle = clock64();
-        } else if (clock64() - t_idle > 4000000000LL) {
-          printf("attention_tc3: issuer stalled (block %d, S items %d/%d, PV items %d/%d chunks %d/%d, done %d of %d)\n",
-                 (int)blockIdx.x, s_k[0], s_k[1], p_k[0], p_k[1], p_cp[0], p_cp[1], done, nitems);
-          __trap();
-        }
+        umma_commit(bO);
+        umma_commit(bar_st(V_EMPTY, st));
       }
     }
     __syncwarp();
   } else {
-    // ================= softmax + epilogue groups (128 threads each, one query row per thread) =================
-    const int grp = (warp - 2) >> 2;
-    const int quarter = warp & 3;
+    // ================= softmax + epilogue: 256 threads per item = (query row) x (key half) =================
+    // Warp (quarter q, half h) of a group owns TMEM lanes [32q, 32q+32) and the score chunks 2h, 2h+1 (keys
+    // [128h, 128h+128)): a single warp cannot keep MUFU busy (two warps per SM sub-partition ran the exponentials
+    // at half the MUFU rate and idled it during their epilogues), four per sub-partition can.  Each warp runs the
+    // online softmax over its own two chunks; the two halves of a row meet once per item, through shared memory,
+    // to agree on the row maximum and the row sum, and each converts half of the 32 output columns.
+    const int sw = warp - 3;
+    const int grp = sw >> 3, half = (sw >> 2) & 1;
+    const int quarter = warp & 3;       // TMEM lane quarter: fixed by hardware to warp id % 4
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // log2(e)/sqrt(32)
-    const bool tr = tracing && quarter == 0 && lane == 0;
+    const bool tr = tracing && quarter == 0 && lane == 0 && half == 0;
     const int b = grp;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * 256;
-    uint32_t zeros[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) zeros[i] = 0u;
-    if (ZERO_S && grp < nitems) {  // this warp's lanes of the whole buffer, before its first S accumulates into them
-#pragma unroll
-      for (int c = 0; c < 8; ++c) tmem_st32(taddr + 32 * c, zeros);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_b(FREE, b));
+    const uint32_t bS = bar_b(S_FULL, b), bO = bar_b(O_FULL, b), bF = bar_b(FREE, b), bP = bar_p(b, 0);
+    // exchange of (m_c, l_c) between the two halves of a row: [item parity][group][half][row] float4
+    float4* xchg = reinterpret_cast<float4*>(smem_al + (sBarB + 16 * 8 - smem_base));
+    const int r_seq = g > 0 ? r / n : 0;  // packed mode: which of the tile's sequences this row belongs to
+    // The two groups would otherwise run in lock-step (same start, same period): both in their exponential phases
+    // (MUFU shared four ways) and then both in their MUFU-free phases (exchange, O wait, epilogue).  Start group 1
+    // about half an item late, so that one group's exponentials run under the other's epilogue.
+    if (grp == 1 && nitems > 2) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < kA4Stagger) {}
     }
     for (int k = grp; k < nitems; k += 2) {
       const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-      const AtItem it = at_decode(items - 1 - ((int)blockIdx.x + k * (int)gridDim.x), n, nseq, g);
-      const int ncols = (it.kv_rows + 15) & ~15;
+      const int idx = item_index(k);
+      const int ncols = item_ncols(k);
       const int npair = (ncols + 63) >> 6;  // 64-key chunks
-      int lo = 0, hi = it.kv_rows;
+      int lo = 0, hi = n;
+      int q_row0, q_rows;
       if (g > 0) {  // packed: this row's own sequence
-        const int sidx = min(r / n, it.q_rows / n - 1);
+        const int unit = idx >> 3;
+        const int cnt = unit == units - 1 ? nseq - unit * g : g;
+        const int sidx = min(r_seq, cnt - 1);
         lo = sidx * n;
         hi = lo + n;
+        q_row0 = unit * g * n;
+        q_rows = cnt * n;
+      } else {
+        const int unit = idx >> 3;
+        q_row0 = (unit >> 1) * n + (unit & 1) * 128;
+        q_rows = min(128, n - (unit & 1) * 128);
       }
       // tcgen05.ld / .st are warp-collective: chunk loops must be warp-uniform, so they run over the union
       // [wlo, whi) of the key ranges of the warp's 32 rows; per-row masks inside.
       const int wlo = __reduce_min_sync(0xffffffffu, lo);
       const int whi = __reduce_max_sync(0xffffffffu, hi);
       const bool uniform = (g == 0);  // split mode: every row of the tile has the same key range
+      auto live = [&](int cp) { return cp < npair && !(64 * cp + 64 <= wlo || 64 * cp >= whi); };
+      auto mask = [&](uint32_t (&u)[32], int c0) {
+        if (!(uniform && c0 + 32 <= hi)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < lo || c0 + i >= hi) u[i] = 0xff800000u;  // -inf
+        }
+      };
+      // 32 scores -> 16 packed bf16 columns of P, stored without waiting
+      auto exps = [&](uint32_t (&u)[32], float msc, unsigned long long& sum2, uint32_t dst) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0 = __uint_as_float(u[i]), x1 = __uint_as_float(u[i + 1]);
+          fma_f32x2(x0, x1, sl2, -msc);
+          if (((i >> 1) & 7) < POLY) {
+            ex2_poly2(x0, x1);
+          } else {
+            x0 = at_ex2(x0);  // masked: 2^-inf = 0
+            x1 = at_ex2(x1);
+          }
+          sum2 = fadd2(sum2, pack_f32x2(x0, x1));
+          pk[i >> 1] = cvt_bf16x2(x0, x1);  // column j of P_c = keys (2j, 2j+1)
+        }
+        tmem_st16_nowait(dst, pk);
+      };
       if (tr) stamp(k, 5);
-      mbar_wait(bar_b(S_FULL, b), ph, 30);
+      mbar_wait(bS, ph, 30);
       fence_after();
       if (tr) stamp(k, 6);
-      // ---- pass 1: the row maximum over the whole score row ----
-      float m_row = -INFINITY;
+      float m_run = -INFINITY;
+      float mc[2] = {-INFINITY, -INFINITY}, lc[2] = {0.f, 0.f};
 #pragma unroll
-      for (int cp = 0; cp < 4; ++cp) {
-        const int c0 = cp * 64;
-        if (cp < npair && !(c0 + 64 <= wlo || c0 >= whi)) {
-          float v[64];
-          tmem_ld64(taddr + c0, v);
-          if (!(uniform && c0 + 64 <= hi)) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
-          }
-          m_row = fmaxf(m_row, at_max64(v));
-        }
-      }
-      const float msc = m_row * sl2;  // every row has at least one key of its own
-      if (tr) stamp(k, 7);
-      // ---- pass 2: P_c = 2^(s * sl2 - msc) per 64-key chunk, bf16 pairs back into the chunk's own columns ----
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int cp = 0; cp < 4; ++cp) {
+      for (int j = 0; j < 2; ++j) {
+        const int cp = 2 * half + j;
         if (cp < npair) {
-          const int c0 = cp * 64;
-          uint32_t pk[32];
-          if (c0 + 64 <= wlo || c0 >= whi) {  // warp-uniform: no row of this warp attends these keys
+          if (live(cp)) {
+            // 96 registers per thread (five warps on a sub-partition) and no spills — local memory misses the
+            // few KB of L1 left beside 160 KB of shared memory and costs an L2 round trip — so only ONE 32-score
+            // piece is held at a time: second piece for its maximum, first piece for its maximum and its
+            // exponentials, second piece again (TMEM loads are cheap with four warps per sub-partition to hide them)
+            const uint32_t tA = taddr + 64 * cp, tB = tA + 32;
+            uint32_t x[32];
+            tmem_ld32_issue(tB, x);
+            tmem_ld_wait32(x);
+            mask(x, 64 * cp + 32);
+            const float mB = at_max32(x);
+            tmem_ld32_issue(tA, x);
+            tmem_ld_wait32(x);
+            mask(x, 64 * cp);
+            const float m_new = fmaxf(m_run, fmaxf(at_max32(x), mB) * sl2);
+            const float msc = (m_new == -INFINITY) ? 0.f : m_new;  // row has no key yet (packed mode)
+            unsigned long long sum2 = pack_f32x2(0.f, 0.f);
+            exps(x, msc, sum2, tA);           // P of keys [0,32) of the chunk -> columns [0,16): consumed scores
+            tmem_ld32_issue(tB, x);
+            tmem_ld_wait32(x);
+            mask(x, 64 * cp + 32);
+            exps(x, msc, sum2, tA + 16);      // keys [32,64) -> columns [16,32): scores of the first piece, consumed
+            float s_lo, s_hi;
+            unpack_f32x2(sum2, s_lo, s_hi);
+            mc[j] = m_new;
+            lc[j] = s_lo + s_hi;
+            m_run = m_new;
+          } else {  // no row of this warp attends these keys
+            uint32_t zeros[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pk[i] = 0u;
-          } else {
-            float v[64];
-            tmem_ld64(taddr + c0, v);
-            if (!(uniform && c0 + 64 <= hi)) {
-#pragma unroll
-              for (int i = 0; i < 64; ++i)
-                if (c0 + i < lo || c0 + i >= hi) v[i] = -INFINITY;
-            }
-#pragma unroll
-            for (int i = 0; i < 64; i += 4) {  // FFMA2 for the scale/shift, MUFU.EX2, FADD2 for the row sum
-              fma_f32x2(v[i], v[i + 1], sl2, -msc);
-              fma_f32x2(v[i + 2], v[i + 3], sl2, -msc);
-              v[i] = at_ex2(v[i]);  // masked: 2^-inf = 0
-              v[i + 1] = at_ex2(v[i + 1]);
-              v[i + 2] = at_ex2(v[i + 2]);
-              v[i + 3] = at_ex2(v[i + 3]);
-              add_f32x2(s0, s1, v[i], v[i + 1]);
-              add_f32x2(s2, s3, v[i + 2], v[i + 3]);
-              pk[i >> 1] = cvt_bf16x2(v[i], v[i + 1]);          // column j of P_c = keys (2j, 2j+1)
-              pk[(i >> 1) + 1] = cvt_bf16x2(v[i + 2], v[i + 3]);
-            }
+            for (int i = 0; i < 32; ++i) zeros[i] = 0u;
+            tmem_st32_nowait(taddr + 64 * cp, zeros);
           }
-          tmem_st32(taddr + c0, pk);                    // P_c over the first half of the chunk's own score columns
-          if (cp == 0) tmem_st32(taddr + 32, zeros);    // O = 0 in the (consumed) second half of chunk 0
+          tmem_st_wait();
           fence_before();
         }
         // (chunks past the item's keys are signalled too: the barrier phases must advance once per item)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p(b, cp));
-        if (tr) stamp(k, 8 + (cp < 3 ? cp : 2));
+        if (lane == 0) mbar_arrive(bP + 8 * cp);
+        if (tr) stamp(k, 7 + j);
       }
-      const float sum = (s0 + s1) + (s2 + s3);
-      // ---- epilogue: O / rowsum -> bf16 ----
-      mbar_wait(bar_b(O_FULL, b), ph, 31);
+      // ---- the two halves of the row agree on the maximum and the sum ----
+      float4* slot = xchg + (((k >> 1) & 1) * 4 + grp * 2) * 128;   // [parity][group] -> [half][row]
+      slot[half * 128 + r] = make_float4(mc[0], lc[0], mc[1], lc[1]);
+      named_bar_sync(1 + grp * 4 + quarter, 64);
+      const float4 other = slot[(half ^ 1) * 128 + r];
+      // chunk order 0..3: this warp's pair sits at [2 half, 2 half + 1] (selects, not indexed stores: registers)
+      const bool h1 = half != 0;
+      float m4[4], l4[4];
+      m4[0] = h1 ? other.x : mc[0];
+      l4[0] = h1 ? other.y : lc[0];
+      m4[1] = h1 ? other.z : mc[1];
+      l4[1] = h1 ? other.w : lc[1];
+      m4[2] = h1 ? mc[0] : other.x;
+      l4[2] = h1 ? lc[0] : other.y;
+      m4[3] = h1 ? mc[1] : other.z;
+      l4[3] = h1 ? lc[1] : other.w;
+      const float m_all = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float fc[4], sum = 0.f;
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        fc[cp] = (m4[cp] == -INFINITY) ? 0.f : at_ex2(m4[cp] - m_all);
+        sum += fc[cp] * l4[cp];
+      }
+      const float inv = 1.0f / sum;
+      if (tr) stamp(k, 9);
+      // ---- epilogue: O = sum_c 2^(m_c - m) O_c / rowsum -> bf16; this warp converts output columns [16 half, +16) ----
+      mbar_wait(bO, ph, 31);
       fence_after();
       if (tr) stamp(k, 11);
       {
-        float o[32];
-        tmem_ld32(taddr + 32, o);
-        if (ZERO_S) {  // score columns back to zero for the buffer's next Q K^T (this warp's lanes only)
-          const int nz = (ncols + 31) >> 5;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < nz) tmem_st32(taddr + 32 * c, zeros);
-        }
-        fence_before();  // O read (and the zero-fill) precede the next S
+        // The four O_c loads together (one round trip), UNCONDITIONALLY: loads guarded by `c < npair` make the
+        // compiler merge "maybe loaded" register arrays through local memory.  Chunks past the item's keys hold
+        // stale columns; their weight is forced to zero by a select, not by a multiplication (0 * NaN).
+        uint32_t o0[16], o1[16], o2[16], o3[16];
+        const uint32_t tO = taddr + 32 + 16 * half;
+        tmem_ld16_issue(tO, o0);
+        tmem_ld16_issue(tO + 64, o1);
+        tmem_ld16_issue(tO + 128, o2);
+        tmem_ld16_issue(tO + 192, o3);
+        tmem_ld_wait16(o0);
+        tmem_ld_wait16(o1);
+        tmem_ld_wait16(o2);
+        tmem_ld_wait16(o3);
+        fence_before();  // the O_c reads precede the next S overwriting the buffer
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_b(FREE, b));  // release TMEM before the global stores
-        const float inv = 1.0f / sum;
-        if (r < it.q_rows) {
-          uint4* dsto = reinterpret_cast<uint4*>(out + (size_t)(it.q_row0 + r) * kN + it.head * kDh);
+        if (lane == 0) mbar_arrive(bF);  // release TMEM before the arithmetic and the global stores
+        float o[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 16; ++i) {
+          const float v1 = 1 < npair ? __uint_as_float(o1[i]) : 0.f;
+          const float v2 = 2 < npair ? __uint_as_float(o2[i]) : 0.f;
+          const float v3 = 3 < npair ? __uint_as_float(o3[i]) : 0.f;
+          float acc = fc[0] * __uint_as_float(o0[i]);
+          acc = fmaf(fc[1], v1, acc);
+          acc = fmaf(fc[2], v2, acc);
+          acc = fmaf(fc[3], v3, acc);
+          o[i] = acc * inv;
+        }
+        if (r < q_rows) {
+          uint4* dsto = reinterpret_cast<uint4*>(out + (size_t)(q_row0 + r) * kN + (idx & 7) * kDh + 16 * half);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
             uint4 u;
-            u.x = cvt_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv);
-            u.y = cvt_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-            u.z = cvt_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-            u.w = cvt_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+            u.x = cvt_bf16x2(o[8 * i], o[8 * i + 1]);
+            u.y = cvt_bf16x2(o[8 * i + 2], o[8 * i + 3]);
+            u.z = cvt_bf16x2(o[8 * i + 4], o[8 * i + 5]);
+            u.w = cvt_bf16x2(o[8 * i + 6], o[8 * i + 7]);
             dsto[i] = u;
           }
         }
@@ -720,13 +811,13 @@ static int at_tensor_map(const void* qkv, uint64_t rows, CUtensorMap* out) {
   return 0;
 }
 
-// CSE_ATTN_VER = 1 keeps the v1 kernel (two issuer warps, P through shared memory, one accumulator per chunk),
-// 3 = v3, 4 = v3 with zero-filled score columns (default; see the v3 header) — for A/B runs.
+// Default: the v1 kernel — still the fastest measured (148 us at 544 x 251 against 174 us for v4, whose groups
+// fall into lock-step: both in their MUFU phases, then both in their MUFU-free phases; profiles/r02_experiments.md).
+// CSE_ATTN_VER=4 selects v4 for A/B runs.
 static int attention_version() {
   static const int ver = []() {
     const char* e = getenv("CSE_ATTN_VER");
-    const int v = e != nullptr ? atoi(e) : 0;
-    return (v == 1 || v == 3 || v == 4) ? v : 4;
+    return (e != nullptr && atoi(e) == 4) ? 4 : 1;
   }();
   return ver;
 }
@@ -738,17 +829,15 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
     set_error("attention_tc: n=%d outside [1,256]", n);
     return 1;
   }
-  // cse_debug_force_mma_attention: 2 = v1, 3 = v3, 4 = v3 + zero-filled scores; otherwise CSE_ATTN_VER
-  const int ver = g_attention_mode == 2 ? 1 : (g_attention_mode == 3 || g_attention_mode == 4) ? g_attention_mode
-                                                                                                : attention_version();
+  // cse_debug_force_mma_attention: 2 = v1, 4 = v4; otherwise CSE_ATTN_VER
+  const int ver = g_attention_mode == 2 ? 1 : g_attention_mode == 4 ? 4 : attention_version();
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAtSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
+      e = cudaFuncSetAttribute(attention_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA2Smem);
+
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return 1;
@@ -767,14 +856,9 @@ int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_
   }
   const int grid = (int)(items < sms ? items : sms);
   if (ver == 4) {
-    launch_pdl(attention_tc3_kernel<true>, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g,
-               (int)items, g_attention_trace);
-    return check_launch("attention_tc3_kernel<1>");
-  }
-  if (ver == 3) {
-    launch_pdl(attention_tc3_kernel<false>, dim3(grid), dim3(kA2Threads), kA2Smem, st, 1, tm, out, n, nseq, g,
-               (int)items, g_attention_trace);
-    return check_launch("attention_tc3_kernel<0>");
+    launch_pdl(attention_tc4_kernel<0>, dim3(grid), dim3(kA4Threads), kA2Smem, st, 1, tm, out, n, nseq, g, (int)items,
+               g_attention_trace);
+    return check_launch("attention_tc4_kernel<0>");
   }
   launch_pdl(attention_tc_kernel, dim3(grid), dim3(kAtThreads), kAtSmem, st, 1, tm, out, n, nseq, g, (int)items);
   return check_launch("attention_tc_kernel");

@@ -225,7 +225,7 @@ int launch_gemm_ln_tc(const float* R, const float* gamma, const float* beta, flo
 // attention.cu
 int launch_attention(const void* qkv, int nseq, int n, int act, void* out, cudaStream_t st);
 int launch_attention_tc(const bf16* qkv, int nseq, int n, bf16* out, cudaStream_t st);  // attention_tc.cu
-extern int g_attention_mode;             // 0 auto, 1 force mma.sync, 2 force tcgen05 v1, 3 / 4 force tcgen05 v3 (4: zero-filled score columns)
+extern int g_attention_mode;             // 0 auto, 1 force mma.sync, 2 force tcgen05 v1, 4 force tcgen05 v4
 extern long long* g_attention_trace;    // attention_tc.cu: optional clock64 trace buffer of CTA 0 (debug)
 // head.cu
 int launch_prelu_ola(const float* X, const float* prelu, int B, int S, int L, int act, void* U,

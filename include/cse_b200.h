@@ -112,7 +112,8 @@ CSE_API const char* cse_last_error(void);
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 CSE_API long long cse_launch_count(void);
 /* Test hook: 0 = automatic choice, 1 = force the mma.sync online-softmax bf16 attention kernel,
- * 2 = force the tcgen05 kernel (n <= 256) — so both kernels can be checked at the same shapes. */
+ * 2 = force the tcgen05 kernel v1 (n <= 256), 4 = force the tcgen05 kernel v4 — so every kernel can be checked at
+ * the same shapes. */
 CSE_API int cse_debug_force_mma_attention(int on);
 /* Debug: device buffer of 64 x 16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64 stamps of its
  * pipeline events (tools/attn_trace.py); NULL turns it off. */
@@ -466,6 +467,20 @@ CSE_API int cse_optim_step(const void* device_table, long long n_chunks, float l
                            float eps, float weight_decay, int amsgrad, float max_norm, int use_scaler,
                            float growth_factor, float backoff_factor, int growth_interval, int write_back_grads,
                            void* state, float* partial, void* stream);
+
+/* ---- evaluation metrics on the device (test.py:198-201,241-245,291-301) ----
+ * cse_sdr: torchmetrics.functional.audio.signal_distortion_ratio(preds, target, use_cg_iter=None,
+ *   filter_length, zero_mean, load_diag) per item, float64 inside: preds, target [B,T] fp32 -> out [B] (dB).
+ *   filter_length <= 1024 (the reference uses the default 512); has_load_diag = 0 means load_diag=None.
+ *   workspace: cse_sdr_workspace_bytes(B, T, filter_length) bytes, 8-byte aligned.
+ * cse_metric_update: the running state of a torchmetrics metric object — acc[0] += sum(values[0..n)),
+ *   acc[1] += n (two doubles in device memory, zero-initialised by the caller); compute() = acc[0] / acc[1].
+ *   SI-SNR values come from cse_tm_si_snr, SDR values from cse_sdr. */
+CSE_API size_t cse_sdr_workspace_bytes(int B, int T, int filter_length);
+CSE_API int cse_sdr(const float* preds, const float* target, int B, int T, int filter_length, int zero_mean,
+                    int has_load_diag, double load_diag, float* out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+CSE_API int cse_metric_update(const float* values, int n, double* acc, void* stream);
 
 #ifdef __cplusplus
 }

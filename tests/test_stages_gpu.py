@@ -108,13 +108,13 @@ def _attention_ref(qkv, nseq, n):
 @pytest.mark.parametrize("nseq,n", [(3, 251), (5, 35), (2, 132), (4, 1), (2, 17), (1, 260), (2, 64),
                                     (7, 35), (300, 35), (40, 252), (1, 128), (3, 129), (2, 256), (5, 100),
                                     (544, 251), (4000, 35), (130, 252), (250, 132), (1001, 67)])
-@pytest.mark.parametrize("prec", [FP32, BF16, "bf16-mma", "bf16-tc", "bf16-tc3", "bf16-tc3z"])
+@pytest.mark.parametrize("prec", [FP32, BF16, "bf16-mma", "bf16-tc", "bf16-tc4"])
 def test_attention(nseq, n, prec):
     """fp32 SIMT kernel, the automatic bf16 choice, and each bf16 kernel forced: tcgen05 (n <= 256;
     packed tiles for n <= 128, split tiles above) and mma.sync online softmax (any n), all against
     the float64 softmax(q k^T / sqrt(d)) v."""
-    # tc = v1 kernel; tc3 = v3 (whole-row maximum, one accumulating O tile, P in TMEM); tc3z = v3 + zero-filled scores
-    mode = {"bf16-mma": 1, "bf16-tc": 2, "bf16-tc3": 3, "bf16-tc3z": 4}.get(prec, 0)
+    # tc = v1 kernel (the default); tc4 = v4 (per-buffer issuers, 16 softmax warps, P in TMEM; opt-in, CSE_ATTN_VER=4)
+    mode = {"bf16-mma": 1, "bf16-tc": 2, "bf16-tc4": 4}.get(prec, 0)
     if mode >= 2 and n > 256:
         pytest.skip("tcgen05 attention handles n <= 256")
     prec = BF16 if mode else prec

@@ -1,10 +1,10 @@
-"""Attention kernel A/B timing + pipeline trace of the tcgen05 v3 kernel (debug tool, not a product path).
+"""Attention kernel A/B timing + pipeline trace of the tcgen05 v4 kernel (debug tool, not a product path).
 
     python tools/attn_trace.py            # on the GPU box
 
 1. CUDA-event timing (20 launches after 3 warm-ups, inputs larger than L2 for the big shapes) of every bf16
-   attention kernel at the shapes of BASELINE configs[1] / [3]:  mma.sync | tcgen05 v1 | tcgen05 v3 | v3 with zero-filled score columns.
-2. clock64 trace of CTA 0 of the v3 kernel (cse_debug_attention_trace) at the intra shape: per item, cycles relative
+   attention kernel at the shapes of BASELINE configs[1] / [3]:  mma.sync | tcgen05 v1 | tcgen05 v4 | v4 with 2/8 and 3/8 polynomial exponentials.
+2. clock64 trace of CTA 0 of the v4 kernel (cse_debug_attention_trace) at the intra shape: per item, cycles relative
    to the item's S issue, so the dead time between the MUFU and tensor phases is visible.
 """
 import ctypes as C
@@ -21,8 +21,8 @@ from cse_b200 import _lib  # noqa: E402
 DEV = "cuda:0"
 TRACE_MODE = int(os.environ.get("ATTN_TRACE_MODE", "4"))
 BF16 = _lib.BF16
-SLOTS = ["S issue", "PV0 issue", "PV1", "PV2", "PV3", "sm wait S", "sm S seen", "sm max done", "sm c0 done", "sm c1 done",
-         "sm c2/3 done", "sm O seen", "sm epi done", "QK load issue", "V load issue", "-"]
+SLOTS = ["S issue", "PV0 issue", "PV1", "PV2", "PV3", "sm wait S", "sm S seen", "sm 1st chunk", "sm 2nd chunk", "sm max/sum xchg",
+         "-", "sm O seen", "sm epi done", "QK load issue", "V load issue", "-"]
 
 
 def run(qkv, nseq, n, out, mode):
@@ -52,8 +52,8 @@ def timeit(nseq, n, mode, iters=20):
 
 
 def main():
-    names = {1: "mma.sync", 2: "tcgen05 v1", 3: "tcgen05 v3", 4: "v3 + zero S"}
-    modes = (1, 2, 3, 4)
+    names = {1: "mma.sync", 2: "tcgen05 v1", 4: "tcgen05 v4"}
+    modes = (1, 2, 4)
     print("shape (nseq x n)          " + "".join(f"{names[m]:>14}" for m in modes) + "   [us per launch]")
     for nseq, n in [(544, 251), (4000, 35), (1040, 252), (2000, 132), (4000, 67), (4000, 19)]:
         row, outs = [], {}
@@ -65,13 +65,13 @@ def main():
                 row.append(f"{'ERR':>14}")
                 print("   ", type(e).__name__, str(e)[:200])
         agree = ""
-        for m in (3, 4):
+        for m in (4,):
             if 1 in outs and m in outs:
                 d = (outs[m].float() - outs[1].float()).norm() / outs[1].float().norm()
                 agree += f"   mode {m} vs mma rel-L2 {d.item():.2e}"
         print(f"{nseq:6d} x {n:3d}             " + "".join(row) + agree)
 
-    # ---- trace of CTA 0, v3 (+ zero-filled scores), intra shape ----
+    # ---- trace of CTA 0, v4, intra shape ----
     nseq, n = 544, 251
     g = torch.Generator(device=DEV).manual_seed(1)
     qkv = (torch.randn(nseq * n, 768, device=DEV, generator=g) * 1.5).to(torch.bfloat16)
