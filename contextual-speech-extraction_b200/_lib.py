@@ -119,6 +119,9 @@ _SIGNATURES = {
     "cse_sdr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "cse_sdr": (C.c_int, [_v, _v, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _v, _v, C.c_size_t, _v]),
     "cse_metric_update": (C.c_int, [_v, C.c_int, _v, _v]),
+    "cse_mix_audio": (C.c_int, [_v] * 8 + [C.c_int, C.c_int, C.c_int, C.c_longlong] + [_v] * 6),
+    "cse_peak_normalize": (C.c_int, [_v, _v, C.c_int, C.c_float, C.c_longlong, _v, _v]),
+    "cse_decimate": (C.c_int, [_v, _v, C.c_int, C.c_longlong, C.c_int, _v, C.c_int, C.c_longlong, _v, _v, _v]),
     "cse_optim_chunk_count": (C.c_longlong, [C.c_int, C.POINTER(C.c_longlong)]),
     "cse_optim_table_fill": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)] + [C.POINTER(_v)] * 5 + [_v, C.c_size_t]),
     "cse_optim_step": (C.c_int, [_v, C.c_longlong] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, C.c_float,

@@ -482,6 +482,29 @@ CSE_API int cse_sdr(const float* preds, const float* target, int B, int T, int f
                     void* stream);
 CSE_API int cse_metric_update(const float* values, int n, double* acc, void* stream);
 
+/* ---- loader-side mixture synthesis + collation on the device ----
+ * Ragged clips come as one flat fp32 buffer per role plus B+1 int64 element offsets (device); outputs are the
+ * collated, zero right-padded [B, T_out] tensors collate_fn builds (dataset_train_CSE.py:507-601).
+ * cse_mix_audio: n_noise = 1 -> mix_audio(signal, noise1, snr1, pad)            (dataset_train_CSE.py:417-456)
+ *                n_noise = 2 -> mix_audio_3spk(signal, noise1, noise2, snr1, snr2, pad)       (:458-505)
+ *   snr1 / snr2: B float64 values on the device (the dataset draws numpy float64 scalars, :257-263).  out_len[b]
+ *   (optional) = samples item b occupies (len(signal), or the longest clip for 3 speakers); T_out must cover it.
+ *   Same dtype promotion as numpy in the reference: float32 energies, float64 gains / mixture / peak scale.
+ * cse_peak_normalize: out[b] = x_b / max|x_b| * peak in float32 (dataset_train_CSE.py:237,274), zero-padded.
+ * cse_decimate: rows of [B, T_in] (valid lengths len_in or NULL) low-pass filtered with taps[n_taps] (device; centre
+ *   tap aligned with the kept samples) and decimated by `down` -> [B, T_out], len_out[b] = ceil(len / down): the
+ *   16 kHz -> 8 kHz step (dataset_train_CSE.py:393-398).  The reference calls librosa.resample, whose soxr back end
+ *   is an absent dependency; the taps are an argument (default of the host mirror: scipy.signal.resample_poly's). */
+CSE_API int cse_mix_audio(const float* signal, const long long* signal_off, const float* noise1,
+                          const long long* noise1_off, const float* noise2, const long long* noise2_off,
+                          const double* snr1, const double* snr2, int B, int n_noise, int pad, long long T_out,
+                          float* mixed, float* signal_out, float* noise1_out, float* noise2_out, int* out_len,
+                          void* stream);
+CSE_API int cse_peak_normalize(const float* x, const long long* off, int B, float peak, long long T_out,
+                               float* out, void* stream);
+CSE_API int cse_decimate(const float* x, const int* len_in, int B, long long T_in, int down, const float* taps,
+                         int n_taps, long long T_out, float* y, int* len_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

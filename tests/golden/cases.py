@@ -85,3 +85,33 @@ def selection_inputs(case):
             est[b, :, s] = 0.7 * src[b, :, perm[s]] + 0.3 * other + 0.05 * torch.randn(T, generator=g)
     ctx_pred = torch.randn(B, n if case["ce"] else 1, generator=g) * 2.0
     return src[:, :, 0].contiguous(), src[:, :, 1:n].contiguous(), est.contiguous(), ctx_pred
+
+
+# Loader-side mixture synthesis (make_golden_mixture.py): name -> (clip lengths, seed, pad).
+# 2 lengths = mix_audio(signal, noise), 3 = mix_audio_3spk(signal, noise1, noise2).
+MIXTURE_CASES = {
+    "2spk_pad_signal_longer": ((2500, 1700), 61, True),
+    "2spk_pad_signal_shorter": ((1600, 2300), 62, True),
+    "2spk_loop_signal_longer": ((2400, 1000), 63, False),
+    "2spk_loop_signal_shorter": ((1500, 2000), 64, False),
+    "3spk_pad": ((1800, 2600, 1200), 65, True),
+    "3spk_loop": ((2000, 900, 2700), 66, False),
+    "3spk_pad_signal_longest": ((2600, 2000, 2100), 67, True),
+}
+
+
+def mixture_case(name):
+    """(clips: list of float32 numpy arrays, peak-normalised to 0.9 like dataset_train_CSE.py:237; snrs: numpy
+    float64 scalars drawn as the dataset draws them, np.clip(N(0, 4), -5, 5); pad)."""
+    import numpy as np
+    lens, seed, pad = MIXTURE_CASES[name]
+    rng = np.random.default_rng(seed)
+    clips = []
+    for n in lens:
+        w = rng.standard_normal(n + 64)
+        x = np.convolve(w, np.ones(8) / 8.0, mode="valid")[:n] * (1.0 + 0.5 * np.sin(np.arange(n) / 97.0))
+        x = x.astype(np.float32)
+        clips.append(x / np.max(np.abs(x)) * 0.9)
+    snrs = [np.clip(rng.normal(0, 4), -5, 5) for _ in range(len(lens) - 1)]
+    assert all(isinstance(s, np.float64) for s in snrs)
+    return clips, snrs, pad

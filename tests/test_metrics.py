@@ -28,7 +28,7 @@ def test_sdr_oracle_agrees_with_time_domain_definition():
 
 def test_sdr_oracle_properties():
     _, src, est = _case(1, 4000, 6)
-    t, p = src[0, :, 0].numpy(), est[0].numpy()
+    t, p = src[0, :, 0].numpy().astype(np.float64), est[0].numpy().astype(np.float64)
     a = MO.signal_distortion_ratio(p, t)
     assert abs(MO.signal_distortion_ratio(3.7 * p, 0.2 * t) - a) < 1e-9          # scale invariance of both arguments
     assert MO.signal_distortion_ratio(t + 1e-4 * p, t) > 60                      # near-perfect estimate
