@@ -493,7 +493,12 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     net = model
     if world > 1:   # the reference's own wrapper (train_ContExt.py:269-273): bucketed NCCL all-reduce overlapped with backward
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, amsgrad=True)      # train_ContSep.py:233
+    fused_opt = args.train_optim == "fused"
+    if fused_opt:   # clip_grad_norm_ + AdamW(amsgrad) in three launches (cse_optim_step), no host sync on the norm
+        from cse_b200.optim import AdamW as FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=1e-4, amsgrad=True)         # train_ContSep.py:233
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, amsgrad=True)
     sisnr = losses.ScaleInvariantSignalNoiseRatio()
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
 
@@ -528,8 +533,11 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     def step(mix, ctx, tgt, module=None):
         opt.zero_grad(set_to_none=True)
         loss = fwd_bwd(module or net, mix, ctx, tgt)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)             # train_ContSep.py:411
-        opt.step()
+        if fused_opt:
+            opt.step(max_norm=5.0)                                          # train_ContSep.py:411-416 in one call
+        else:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)         # train_ContSep.py:411
+            opt.step()
         return loss
 
     def step_device():
@@ -671,6 +679,9 @@ def main():
     ap.add_argument("--train-seconds", type=int, default=SECONDS, help="--workload train: mixture length (4; 16 = max_sp_len cap)")
     ap.add_argument("--train-loss", default="sisnr", choices=["sisnr", "pit"],
                     help="--workload train: ContExt -SI-SNR (train_ContExt.py:367) or ContSep PIT + selector CE (train_ContSep.py:391-394)")
+    ap.add_argument("--train-optim", default="fused", choices=["fused", "torch"],
+                    help="fused: cse_b200.optim.AdamW (clip + AdamW(amsgrad) in three launches); torch: stock "
+                         "clip_grad_norm_ + torch.optim.AdamW as the reference calls them")
     ap.add_argument("--train-precision", default="autocast", choices=["autocast", "fp32"],
                     help="training leg: torch.autocast(bf16) like the reference's --bf16 (tensor-core layers), or the fp32 parity kernels")
     ap.add_argument("--train-ragged", action="store_true",

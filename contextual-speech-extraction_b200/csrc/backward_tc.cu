@@ -101,8 +101,9 @@ int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, con
   if (dW != nullptr) {
     if (launch_transpose_cast(dC, 0, N, M, N, Mpad, s.XT, st)) return 1;     // (dC^T) [N, Mpad]
     if (launch_transpose_cast(A, a_is_bf16, lda, M, K, Mpad, s.YT, st)) return 1;  // (A^T) [K, Mpad]
-    // dW[N,K] += XT YT^T : in-place accumulation through the TMA reduce-add epilogue
-    if (launch_gemm_tc(s.XT, Mpad, s.YT, nullptr, 0.f, dW, dW, K, N, K, Mpad, 0, 1, st)) return 1;
+    // dW[N,K] += XT YT^T : in-place accumulation through the TMA reduce-add epilogue, the token dimension split
+    // over the CTA pairs (2-8 output tiles alone would leave 140 SMs idle)
+    if (launch_gemm_tc_splitk(s.XT, Mpad, s.YT, Mpad, dW, K, N, K, Mpad, st)) return 1;
   }
   return 0;
 }

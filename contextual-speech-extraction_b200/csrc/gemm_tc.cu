@@ -116,7 +116,7 @@ __global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
-               int relu) {
+               int relu, int ksplit) {
   using Cfg = TcCfg<BN, PAIR, ARES>;
   pdl_launch_dependents();
   static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
@@ -140,13 +140,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kTM - 1) / kTM, n_tiles = N / BN;
   const int num_kb = K / kTK;
+  // Split-K (ksplit > 1; wgrad: few output tiles, K = the row count): a tile job covers k-blocks
+  // [ks * kb_per, min(num_kb, (ks + 1) * kb_per)) and the jobs of one tile meet in C through the reduce-add
+  // epilogue.  The host picks ksplit so that no job is empty and only with accumulate_into_c and no bias.
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
   // CTA pairs (clusters of 2): both CTAs of a pair walk the same n-tile sequence on adjacent
   // m-tiles, so every weight tile is fetched from L2 ONCE per pair — each CTA loads half of it and
   // TMA-multicasts that half into both CTAs' shared memory.  (These GEMMs were bound by L2->SM
   // bandwidth, ~9 TB/s aggregate, because the weights are re-streamed for every 128-row tile.)
   const int cta_rank = (int)cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int total_pt = ((m_tiles + 1) >> 1) * n_tiles;
+  const int total_pt = ((m_tiles + 1) >> 1) * n_tiles * ksplit;
   // Tile walk.  Default: pair p takes tiles p, p + npairs, ... (n fastest, so the pairs that share an
   // A tile run at the same time).  ARES: pair p takes a CONTIGUOUS run of tiles, so consecutive tiles
   // share their row tile and A is (re)loaded only when the row tile changes.
@@ -186,9 +190,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The whole warp walks the loop (keeps it convergent for the teardown barrier); lane 0 acts.
     uint32_t stage = 0, phase = 0, seg = 0;
     for (int pt = t_begin; pt < t_end; pt += t_step) {
-      const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
+      const int tl = pt / ksplit, ks = pt - tl * ksplit;
+      const int m0 = (2 * (tl / n_tiles) + cta_rank) * kTM, n0 = (tl % n_tiles) * BN;
       const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         if constexpr (ARES) {
           if (lane == 0) {
             if (new_rows) {  // k-block kb of the previous row tile has been consumed by its last MMA
@@ -239,7 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();
       const uint32_t d_tmem = tmem_base + astage * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int ks = pt % ksplit;
+      const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (lane == 0) {
           if (new_rows) mbar_wait_spin(bar_afull + 8 * kb, seg & 1u, 6);
           mbar_wait_spin(bar_full + 8 * stage, phase, 3);
@@ -250,8 +258,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kTK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
 #ifndef CSE_DBG_NOMMA
-            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
 #endif
           }
           // release the stage in both CTAs
@@ -294,9 +302,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bv[i + 3] = b4.w;
       }
     };
-    if (bias != nullptr && t_begin < t_end) load_bias((t_begin % n_tiles) * BN + cgroup * GW);
+    if (bias != nullptr && t_begin < t_end) load_bias((t_begin % n_tiles) * BN + cgroup * GW);  // (bias: ksplit == 1)
     for (int pt = t_begin; pt < t_end; pt += t_step) {
-      const int m0 = (2 * (pt / n_tiles) + cta_rank) * kTM, n0 = (pt % n_tiles) * BN;
+      const int tl = pt / ksplit;
+      const int m0 = (2 * (tl / n_tiles) + cta_rank) * kTM, n0 = (tl % n_tiles) * BN;
       const int row_base = m0 + quarter * 32;
       mbar_wait(bar_tfull + 8 * astage, aphase, 4);
       tc_fence_after();
@@ -493,7 +502,7 @@ int sm_count() {  // of the CURRENT device (cached per ordinal)
 template <int BN, bool OUT_F32, bool PAIR, bool ARES = false>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
-                          int N, int K, int relu, cudaStream_t st) {
+                          int N, int K, int relu, cudaStream_t st, int ksplit = 1) {
   using Cfg = TcCfg<BN, PAIR, ARES>;
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
@@ -505,12 +514,12 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     }
     once.mark_configured();
   }
-  const int pair_tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN);
+  const int pair_tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN) * ksplit;
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
   cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
-                                      accumulate, C, ldc, M, N, K, relu);
+                                      accumulate, C, ldc, M, N, K, relu, ksplit);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
     return 1;
@@ -565,6 +574,35 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
   }
   return out_fp32 ? launch_tc_impl<128, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
                   : launch_tc_impl<128, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+}
+
+// C[M,N] (fp32) += A[M,K] W[N,K]^T with the K dimension split over CTAs: the weight-gradient shape (M, N = a layer's
+// out / in features, K = the token count), whose 2-8 output tiles would otherwise occupy 2-8 of the 148 SMs.
+int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float* C, int ldc, int M, int N, int K,
+                          cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (K % kTK != 0 || N % 128 != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldc % 8 != 0) {
+    set_error("gemm_tc_splitk: need K %% 64 == 0, N %% 128 == 0, lda/ldw/ldc %% 8 == 0 (M=%d N=%d K=%d)", M, N, K);
+    return 1;
+  }
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) {
+    set_error("gemm_tc_splitk: operands must be 16-byte aligned");
+    return 1;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB, tmC;
+  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
+  if (get_tensor_map(W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2), kTK, 2, &tmB)) return 1;
+  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CSE_EPI_ROW_BYTES / 4, 4, &tmC)) return 1;
+  const int num_kb = K / kTK;
+  const int tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN);
+  int want = (sm_count() / 2) / tiles;              // one job per CTA pair
+  if (want > num_kb / 4) want = num_kb / 4;         // at least four k-blocks (one ring) per job
+  if (want < 1) want = 1;
+  const int kb_per = ceil_div(num_kb, want);
+  const int ksplit = ceil_div(num_kb, kb_per);      // no empty job
+  return BN == 256 ? launch_tc_impl<256, true, false>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit)
+                   : launch_tc_impl<128, true, false>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit);
 }
 
 }  // namespace cse
