@@ -192,6 +192,18 @@ static bool ffn_fused_enabled() {
   return on;
 }
 
+// CSE_OUTPROJ_LN=1 runs out-proj (+R) and norm2 as ONE kernel (cse_linear_residual_ln: LayerNorm in the GEMM
+// epilogue).  Off by default: correct and 32 launches / 4.5 GB of HBM reads per forward lighter, but measured 95 us
+// against 58 + 38 us for the two kernels it replaces — its epilogue is a chain of TMEM round trips
+// (profiles/r02_experiments.md section 2).
+static bool outproj_ln_fused_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_OUTPROJ_LN");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 // CSE_LN_FUSED=1 runs norm1 -> in_proj as one kernel (gemm_ln_tc.cu).  Off by default: measured 123-132 us
 // against 36 + 67 us for the two kernels (its LayerNorm warps cannot keep enough loads in flight inside the
 // 96 registers a 576-thread CTA leaves them), profiles/r01_experiments.md.
@@ -227,9 +239,16 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
                  3 * kN, kN, 0, 0, st)) return 1;
     }
     if (launch_attention(QKV, nseq, n, act, AO, st)) return 1;
-    if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
-               0, 1, st)) return 1;
-    if (launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+    if (pl.precision == CSE_BF16 && outproj_ln_fused_enabled()) {
+      // x = x + out_proj(attention); norm2(x) in the same kernel: the row is normalised while it is on chip
+      CSE_REQUIRE(lp.out_proj_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
+      if (launch_gemm_tc_residual_ln((const bf16*)AO, kN, (const bf16*)lp.out_proj_w_bf16, lp.out_proj_b, R,
+                                     lp.ln2_g, lp.ln2_b, 1e-6f, (bf16*)H, M, kN, st)) return 1;
+    } else {
+      if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
+                 0, 1, st)) return 1;
+      if (launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+    }
     if (pl.precision == CSE_BF16 && ffn_fused_enabled()) {
       // Linear -> ReLU -> Linear -> residual add in one kernel: the [M,1024] hidden never leaves the SM
       CSE_REQUIRE(lp.ffn1_w_bf16 && lp.ffn2_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
@@ -682,6 +701,14 @@ int cse_ln_linear(const float* R, const float* gamma, const float* beta, float e
   CSE_REQUIRE(R && gamma && beta && W_bf16 && C, "ln_linear: NULL argument");
   return launch_gemm_ln_tc(R, gamma, beta, eps, (const bf16*)W_bf16, bias, (bf16*)C, ldc, M, N, relu,
                            (cudaStream_t)stream);
+}
+
+int cse_linear_residual_ln(const void* A_bf16, int lda, const void* W_bf16, const float* bias, float* R,
+                           const float* gamma, const float* beta, float eps, void* H_bf16, int M, int K,
+                           void* stream) {
+  CSE_REQUIRE(A_bf16 && W_bf16 && bias && R && gamma && beta && H_bf16, "linear_residual_ln: NULL argument");
+  return launch_gemm_tc_residual_ln((const bf16*)A_bf16, lda, (const bf16*)W_bf16, bias, R, gamma, beta, eps,
+                                    (bf16*)H_bf16, M, K, (cudaStream_t)stream);
 }
 
 int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,

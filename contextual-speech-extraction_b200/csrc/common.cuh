@@ -217,6 +217,8 @@ int launch_gemm_simt(const float* A, int lda, const float* W, const float* bias,
 int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, float bias_scale,
                    const float* residual, void* C, int ldc, int M, int N, int K, int relu,
                    int out_fp32, cudaStream_t st);
+int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const float* bias, float* R, const float* gamma,
+                               const float* beta, float eps, bf16* H, int M, int K, cudaStream_t st);
 int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float* C, int ldc, int M, int N, int K,
                           cudaStream_t st);  // C (fp32) += A W^T, K split over the CTA pairs (wgrad)
 // gemm_ln_tc.cu: C(bf16) = act(LN(R) W^T + bias), K = 256

@@ -90,9 +90,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return tc
 // (4 k-blocks, 64 KB) while the CTA walks the n-tiles of its rows, so A crosses the L2 once per row tile
 // instead of once per (row tile, n-tile); the ring stages then hold weight tiles only.  These GEMMs are
 // bound by L2 throughput (~10 TB/s for operand loads + output stores together), not by HBM or the MMAs.
-template <int BN, bool PAIR, bool ARES = false>
+template <int BN, bool PAIR, bool ARES = false, bool LNE = false>
 struct TcCfg {
-  static constexpr int kStages = PAIR ? CSE_PAIR_STAGES : ((BN == 256) ? CSE_STAGES_256 : 6);
+  // LNE (K = 256: four k-blocks per tile, an epilogue-bound kernel): three ring stages are enough, and the 48 KB
+  // they free hold the bias / gamma / beta vectors (read from global memory per piece they cost an L2 round trip
+  // each: the L1 left beside 225 KB of shared memory does not keep them)
+  static constexpr int kStages = LNE ? 3 : (PAIR ? CSE_PAIR_STAGES : ((BN == 256) ? CSE_STAGES_256 : 6));
   static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kTK * 2;
   static constexpr int kAStages = ARES ? 4 : kStages;  // ARES: one slot per k-block of the resident tile
@@ -108,16 +111,31 @@ struct TcCfg {
   static constexpr int kEpiBufBytes = 32 * kRowBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
   static constexpr int kRingBytes = kAStages * kABytes + kStages * kBBytes;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kRingBytes + kEpiBytes + 384;
+  static constexpr int kVecBytes = LNE ? 3 * 256 * 4 : 0;   // bias, gamma, beta
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kRingBytes + kEpiBytes + 384 + kVecBytes;
 };
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES>
-__global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES>::kThreads), 1)
+// LNE (BN = 256 = N, fp32 residual stream): the epilogue is `R += A W^T + b; H = LayerNorm(R)` — the attention
+// output projection, its residual add and the pre-FFN LayerNorm of a transformer layer in one kernel
+// (CSE_transformer.py:399-408).  Unfused, LayerNorm re-reads the 140 MB residual stream the projection has just
+// written; here the row is normalised while it is on chip.
+struct LnEpilogue {
+  float* R;            // [M,256] fp32 residual stream, updated in place
+  const float* gamma;  // LayerNorm weight / bias
+  const float* beta;
+  bf16* H;             // [M,256] bf16 LayerNorm(R_new)
+  float eps;
+};
+
+template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false>
+__global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES, LNE>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
-               int relu, int ksplit) {
-  using Cfg = TcCfg<BN, PAIR, ARES>;
+               int relu, int ksplit, LnEpilogue ln) {
+  using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
+  static_assert(!LNE || (BN == 256 && OUT_F32 && !PAIR && !ARES && Cfg::kEpiWarps == 8),
+                "the LayerNorm epilogue is built on the 256-wide fp32 per-CTA variant");
   pdl_launch_dependents();
   static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
@@ -134,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_afull = bar_tempty + 16;   // ARES: [4] resident-A k-block landed
   const uint32_t bar_aempty = bar_afull + 32;   // ARES: [4] resident-A k-block no longer read by any MMA
   const uint32_t tmem_slot = bar_aempty + 32;
+  const uint32_t sVec = sBar + 384;  // LNE: bias[256], gamma[256], beta[256]
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
@@ -178,6 +197,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);  // same warp id in both CTAs
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
+  if constexpr (LNE) {  // parameters, not produced by the previous kernel: may be read before pdl_wait()
+    float* vec = reinterpret_cast<float*>(smem_aligned + (sVec - smem_base));
+    for (int i = threadIdx.x; i < 256; i += Cfg::kThreads) {
+      vec[i] = bias[i];
+      vec[256 + i] = ln.gamma[i];
+      vec[512 + i] = ln.beta[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
@@ -194,6 +221,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (2 * (tl / n_tiles) + cta_rank) * kTM, n0 = (tl % n_tiles) * BN;
       const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
       const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      if constexpr (LNE) {
+        // the residual rows this tile's epilogue will read, one tile of lead: HBM -> L2 now, so that the epilogue's
+        // loads are L2 hits (its eight warps cannot keep enough HBM requests in flight themselves)
+        const int rows_here = min(kTM, M - m0);
+        const char* rbase = reinterpret_cast<const char*>(ln.R + (size_t)m0 * kN);
+        for (int i = lane; i < rows_here * (kN * 4 / 128); i += 32)
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(rbase + (size_t)i * 128));
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         if constexpr (ARES) {
           if (lane == 0) {
@@ -307,13 +342,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tl = pt / ksplit;
       const int m0 = (2 * (tl / n_tiles) + cta_rank) * kTM, n0 = (tl % n_tiles) * BN;
       const int row_base = m0 + quarter * 32;
+      float4 rq[LNE ? 8 : 1];  // LNE: the next 32 x 32 piece of the residual stream, in the coalesced walk's layout
+      if constexpr (LNE) {     // (does not depend on the accumulator: requested before waiting for it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = row_base + 4 * i + (lane >> 3);
+          rq[i] = r < M ? *reinterpret_cast<const float4*>(ln.R + (size_t)r * kN + cgroup * 128 + 4 * (lane & 7))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       mbar_wait(bar_tfull + 8 * astage, aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + astage * BN;
+      if constexpr (LNE) {
+        // One output row per thread pair: this thread holds columns [128 cgroup, +128) of row `row` (TMEM lane =
+        // row).  Global memory is touched row-contiguously instead — a 32-row x 32-column piece goes through the
+        // warp's 4 KB staging tile both ways (a first version with each lane walking its own row issued 32
+        // separate lines per load instruction and was 40 us slower than the two kernels it replaces):
+        //   pass 1: R piece -> staging -> x = acc + b + R -> staging -> R;  x parked in the accumulator's own TMEM
+        //           columns; half-row sums of (x - shift) and (x - shift)^2 -> half-row mean and M2; the two halves
+        //           of a row meet through shared memory and combine (Chan)
+        //   pass 2: x from TMEM -> (x - mean) rstd gamma + beta -> bf16 -> staging -> H
+        const float* s_vec = reinterpret_cast<const float*>(smem_aligned + (sVec - smem_base));
+        float4* stg4 = reinterpret_cast<float4*>(stg0_ptr);          // [32 rows][8 x 16 B], slot ^ (row & 7)
+        const int cr = lane >> 3, cc = lane & 7;                       // coalesced walk: 4 rows x 128 B per step
+        float s1 = 0.f, s2 = 0.f, shift = 0.f;  // sums of (x - shift), (x - shift)^2; shift = the half-row's first x
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = cgroup * 128 + ch * 32;
+          float v[32];
+          tmem_ld32(t_row + col, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stg4[(4 * i + cr) * 8 + (cc ^ ((4 * i + cr) & 7))] = rq[i];
+          if (ch < 3) {  // the next piece's loads fly while this one is processed
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = row_base + 4 * i + cr;
+              rq[i] = r < M ? *reinterpret_cast<const float4*>(ln.R + (size_t)r * kN + col + 32 + 4 * cc)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          __syncwarp();
+          uint32_t xb[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = stg4[lane * 8 + (j ^ (lane & 7))];
+            const float4 b4 = *reinterpret_cast<const float4*>(s_vec + col + 4 * j);
+            float4 x;
+            x.x = (v[4 * j] + b4.x) + r4.x;
+            x.y = (v[4 * j + 1] + b4.y) + r4.y;
+            x.z = (v[4 * j + 2] + b4.z) + r4.z;
+            x.w = (v[4 * j + 3] + b4.w) + r4.w;
+            if (ch == 0 && j == 0) shift = x.x;
+            const float d0 = x.x - shift, d1 = x.y - shift, d2 = x.z - shift, d3 = x.w - shift;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            stg4[lane * 8 + (j ^ (lane & 7))] = x;
+            xb[4 * j] = __float_as_uint(x.x);
+            xb[4 * j + 1] = __float_as_uint(x.y);
+            xb[4 * j + 2] = __float_as_uint(x.z);
+            xb[4 * j + 3] = __float_as_uint(x.w);
+          }
+          tmem_st32(t_row + col, xb);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = row_base + 4 * i + cr;
+            const float4 x = stg4[(4 * i + cr) * 8 + (cc ^ ((4 * i + cr) & 7))];
+            if (r < M) *reinterpret_cast<float4*>(ln.R + (size_t)r * kN + col + 4 * cc) = x;
+          }
+          __syncwarp();  // the staging tile is rewritten by the next piece
+        }
+        // half-row mean and M2 from the shifted sums (the shift is a sample of the row: no cancellation)
+        const float mean_h = shift + s1 * (1.0f / 128.f);
+        const float m2 = fmaxf(s2 - s1 * s1 * (1.0f / 128.f), 0.f);
+        // (mean, M2) of this half-row -> the upper 2 KB of this warp's staging tile (pass 3 uses the lower 2 KB
+        // only; the next tile's pass 1 is behind the barrier at the end of the tile); the partner warp — same lane
+        // quarter, other column half, four warps away — reads it from there
+        float2* xch_mine = reinterpret_cast<float2*>(stg0_ptr + 2048);
+        const int partner = (warp - 2) ^ 4;
+        const float2* xch_other = reinterpret_cast<const float2*>(
+            smem_aligned + (sEpi - smem_base) + partner * Cfg::kEpiBufs * Cfg::kEpiBufBytes + 2048);
+        xch_mine[lane] = make_float2(mean_h, m2);
+        named_bar_sync(1 + quarter, 64);  // the two warps of this lane quarter
+        const float2 o = xch_other[lane];
+        const float mean = 0.5f * (mean_h + o.x);
+        const float dm = mean_h - o.x;
+        const float var = (m2 + o.y + dm * dm * 64.f) * (1.0f / 256.f);
+        const float rstd = rsqrtf(var + ln.eps);
+        uint4* stgh = reinterpret_cast<uint4*>(stg0_ptr);               // [32 rows][4 x 16 B], slot ^ ((row >> 1) & 3)
+        const int hr = lane >> 2, hc = lane & 3;                       // coalesced walk: 8 rows x 64 B per step
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = cgroup * 128 + ch * 32;
+          float v[32];
+          tmem_ld32(t_row + col, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 g0 = *reinterpret_cast<const float4*>(s_vec + 256 + col + 8 * j);
+            const float4 g1 = *reinterpret_cast<const float4*>(s_vec + 256 + col + 8 * j + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_vec + 512 + col + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_vec + 512 + col + 8 * j + 4);
+            const float* x = v + 8 * j;
+            uint4 u;
+            u.x = cvt_bf16x2((x[0] - mean) * rstd * g0.x + b0.x, (x[1] - mean) * rstd * g0.y + b0.y);
+            u.y = cvt_bf16x2((x[2] - mean) * rstd * g0.z + b0.z, (x[3] - mean) * rstd * g0.w + b0.w);
+            u.z = cvt_bf16x2((x[4] - mean) * rstd * g1.x + b1.x, (x[5] - mean) * rstd * g1.y + b1.y);
+            u.w = cvt_bf16x2((x[6] - mean) * rstd * g1.z + b1.z, (x[7] - mean) * rstd * g1.w + b1.w);
+            stgh[lane * 4 + (j ^ ((lane >> 1) & 3))] = u;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + hr, r = row_base + rr;
+            const uint4 u = stgh[rr * 4 + (hc ^ ((rr >> 1) & 3))];
+            if (r < M) *reinterpret_cast<uint4*>(ln.H + (size_t)r * kN + col + 8 * hc) = u;
+          }
+          __syncwarp();
+        }
+        named_bar_sync(1 + quarter, 64);  // the exchange slots are rewritten by the next tile
+      }
 #ifdef CSE_DBG_NOEPI
       constexpr int kNch = 0;
 #else
-      constexpr int kNch = NCH;
+      constexpr int kNch = LNE ? 0 : NCH;
 #endif
 #pragma unroll 1
       for (int ch = 0; ch < kNch; ++ch, ++chunk_ctr) {
@@ -499,14 +651,14 @@ int sm_count() {  // of the CURRENT device (cached per ordinal)
   return n;
 }
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES = false>
+template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
-                          int N, int K, int relu, cudaStream_t st, int ksplit = 1) {
-  using Cfg = TcCfg<BN, PAIR, ARES>;
+                          int N, int K, int relu, cudaStream_t st, int ksplit = 1, LnEpilogue ln = LnEpilogue{}) {
+  using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
@@ -518,8 +670,8 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
-                                      accumulate, C, ldc, M, N, K, relu, ksplit);
+  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
+                                      accumulate, C, ldc, M, N, K, relu, ksplit, ln);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
     return 1;
@@ -574,6 +726,30 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
   }
   return out_fp32 ? launch_tc_impl<128, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
                   : launch_tc_impl<128, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+}
+
+// R[M,256] += A[M,K] W[256,K]^T + b in place, H[M,256] = LayerNorm(R) (bf16): out-proj + residual + norm2 of a
+// transformer layer in one kernel (CSE_transformer.py:399-408).
+int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const float* bias, float* R, const float* gamma,
+                               const float* beta, float eps, bf16* H, int M, int K, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (K % kTK != 0 || lda % 8 != 0) {
+    set_error("gemm_tc_residual_ln: need K %% 64 == 0 and lda %% 8 == 0 (K=%d lda=%d)", K, lda);
+    return 1;
+  }
+  if (A == nullptr || W == nullptr || bias == nullptr || R == nullptr || gamma == nullptr || beta == nullptr || H == nullptr) {
+    set_error("gemm_tc_residual_ln: NULL argument");
+    return 1;
+  }
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)R | (uintptr_t)H | (uintptr_t)bias | (uintptr_t)gamma | (uintptr_t)beta) & 15) {
+    set_error("gemm_tc_residual_ln: operands must be 16-byte aligned");
+    return 1;
+  }
+  CUtensorMap tmA, tmB;
+  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
+  if (get_tensor_map(W, (uint64_t)kN, (uint64_t)K, (uint64_t)K, 128, kTK, 2, &tmB)) return 1;  // half tile per CTA
+  LnEpilogue ln{R, gamma, beta, H, eps};
+  return launch_tc_impl<256, true, false, false, true>(tmA, tmB, tmA /*unused*/, bias, 1.f, 0, R, kN, M, kN, K, 0, st, 1, ln);
 }
 
 // C[M,N] (fp32) += A[M,K] W[N,K]^T with the K dimension split over CTAs: the weight-gradient shape (M, N = a layer's

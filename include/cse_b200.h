@@ -221,6 +221,15 @@ CSE_API int cse_linear(const void* A, int lda, const void* W, const float* bias,
 CSE_API int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                           const float* b2, float* R, int M, void* stream);
 
+/* Attention output projection + residual add + pre-FFN LayerNorm in one tcgen05 kernel (CSE_transformer.py:399-408:
+ * `src = src + self_att(...)` then `norm2(src)`), CSE_BF16 only:
+ *   R[M,256] (fp32, in place) += A[M,K] W[256,K]^T + bias;   H[M,256] (bf16) = LayerNorm(R; gamma, beta, eps)
+ * A, W bf16 (K % 64 == 0).  The GEMM epilogue reads and writes the residual row straight from / to global memory
+ * and normalises it while it is on chip, so the stream is not re-read by a separate LayerNorm kernel. */
+CSE_API int cse_linear_residual_ln(const void* A_bf16, int lda, const void* W_bf16, const float* bias, float* R,
+                                   const float* gamma, const float* beta, float eps, void* H_bf16, int M, int K,
+                                   void* stream);
+
 /* Pre-norm sub-block head `norm(src)` -> Linear fused (CSE_transformer.py:385-390 norm1 -> in_proj,
  * :407-411 norm2 -> ffn.0 + ReLU), CSE_BF16 only: C[M,N] bf16 = act(LN(R[M,256]) W[N,256]^T + bias),
  * N % 256 == 0.  The fp32 residual row is read once; LayerNorm runs in the GEMM's A-operand producer warps. */

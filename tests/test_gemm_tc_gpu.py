@@ -78,6 +78,29 @@ def test_ln_fused_gemm(M, N, relu):
     assert rel_l2(out.float().cpu(), ref) < 5e-3
 
 
+@pytest.mark.parametrize("M,K", [(1, 256), (128, 256), (129, 256), (517, 256), (20000, 256), (2 * 148 * 128 + 77, 256),
+                                 (136544, 256), (1000, 64), (777, 1024)])
+def test_linear_residual_ln(M, K):
+    """cse_linear_residual_ln == out-proj GEMM + residual add + LayerNorm kernel (`src = src + att; norm2(src)`,
+    CSE_transformer.py:399-408): R against fp64, H against fp64 LayerNorm of OUR fp32 R (bf16 output rounding)."""
+    A = _rand(M, K, seed=31).to(torch.bfloat16)
+    W = (_rand(256, K, seed=32) / (K ** 0.5)).to(torch.bfloat16)
+    bias, R0 = _rand(256, seed=33), _rand(M, 256, seed=34) * 2.0 + 0.5
+    g, b = 1 + 0.1 * _rand(256, seed=35), 0.1 * _rand(256, seed=36)
+    Ad, Wd, biasd, gd, bd = A.to(DEV), W.to(DEV), bias.to(DEV), g.to(DEV), b.to(DEV)
+    Rd = R0.to(DEV).clone()
+    H = torch.zeros(M, 256, dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_linear_residual_ln", _lib.ptr(Ad), K, _lib.ptr(Wd), _lib.ptr(biasd), _lib.ptr(Rd), _lib.ptr(gd),
+              _lib.ptr(bd), 1e-6, _lib.ptr(H), M, K, _st())
+    torch.cuda.synchronize()
+    ref_R = R0.double() + A.double() @ W.double().t() + bias.double()
+    assert rel_l2(Rd.cpu(), ref_R) < 2e-6
+    x = Rd.cpu().double()
+    ln = (x - x.mean(-1, keepdim=True)) / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-6) * g.double() + b.double()
+    assert rel_l2(H.float().cpu(), ln) < 3e-3                                  # bf16 rounding of the output only
+    assert (H.float().cpu() - ln).abs().max() < 0.04
+
+
 @pytest.mark.parametrize("M", [1, 128, 129, 517, 20000, 2 * 148 * 128 + 77, 3 * 148 * 128 + 5])
 def test_ffn_fused(M):
     """cse_ffn_fused == Linear(256,1024) -> ReLU -> bf16 -> Linear(1024,256) -> residual add
