@@ -104,6 +104,7 @@ _SIGNATURES = {
                                  _v, _v]),
     "cse_layernorm_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_float, C.c_int, _v, _v, _v, _v]),
     "cse_attention_bwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v]),
+    "cse_attention_bwd_bf16": (C.c_int, [_v, _v, _v, C.c_int, C.c_int, _v, _v]),
     "cse_groupnorm_fwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, C.c_float, _v, _v, _v, _v]),
     "cse_groupnorm_bwd": (C.c_int, [_v, _v, _v, _v, C.c_int, C.c_int, _v, _v, _v, _v, _v]),
     "cse_sequences_to_chunks": (C.c_int, [_v, C.c_int, C.c_int, C.c_int, C.c_int, _v, _v, _v]),

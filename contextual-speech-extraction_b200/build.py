@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcse_b200.so")
 SOURCES = ["abi.cu", "frontend.cu", "norm.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu",
            "attention_tc.cu", "gemm_ln_tc.cu", "ffn_tc.cu", "head.cu", "loss.cu", "backward.cu",
-           "backward_abi.cu", "train_ops.cu", "backward_tc.cu", "optim.cu", "metrics.cu", "mixture.cu"]
+           "backward_abi.cu", "train_ops.cu", "backward_tc.cu", "optim.cu", "metrics.cu", "mixture.cu", "attention_bwd_mma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: the fp32 parity mode needs IEEE division / sqrt / expf
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -27,7 +27,7 @@ def _stale(target, deps):
 
 
 def build_library(force=False, verbose=False):
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "cse_b200.h"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(CSRC, "mma_sync.cuh"), os.path.join(HERE, "..", "include", "cse_b200.h"),
                os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in SOURCES:

@@ -117,6 +117,13 @@ int cse_attention_bwd(const float* qkv, const float* out, const float* d_out, in
   return launch_attention_bwd(qkv, out, d_out, nseq, n, d_qkv, (cudaStream_t)stream);
 }
 
+int cse_attention_bwd_bf16(const void* qkv_bf16, const void* out_bf16, const float* d_out, int nseq, int n,
+                           float* d_qkv, void* stream) {
+  CSE_REQUIRE(qkv_bf16 && out_bf16 && d_out && d_qkv, "attention_bwd_bf16: NULL argument");
+  return launch_attention_bwd_bf16((const bf16*)qkv_bf16, (const bf16*)out_bf16, d_out, nseq, n, d_qkv,
+                                   (cudaStream_t)stream);
+}
+
 size_t cse_layer_workspace_bytes(int nseq, int n) {
   if (nseq <= 0 || n <= 0) return 0;
   return carve_layer_ws(nullptr, (size_t)nseq * n).total;

@@ -12,6 +12,8 @@
 // split over M (several launches accumulating through the TMA reduce-add epilogue, or native MN-major UMMA
 // operands) is the follow-up once this is measured.
 // Reference: autograd of nn.Linear (CSE_transformer.py:335-340,468-477; ContSep.py:229,247,255,258).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cse {
@@ -99,11 +101,32 @@ int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, con
     if (launch_gemm_tc(s.dC16, N, s.WT16, nullptr, 0.f, nullptr, dA, ldda, M, K, N, 0, dA_fp32 ? 1 : 0, st)) return 1;
   }
   if (dW != nullptr) {
-    if (launch_transpose_cast(dC, 0, N, M, N, Mpad, s.XT, st)) return 1;     // (dC^T) [N, Mpad]
-    if (launch_transpose_cast(A, a_is_bf16, lda, M, K, Mpad, s.YT, st)) return 1;  // (A^T) [K, Mpad]
-    // dW[N,K] += XT YT^T : in-place accumulation through the TMA reduce-add epilogue, the token dimension split
-    // over the CTA pairs (2-8 output tiles alone would leave 140 SMs idle)
-    if (launch_gemm_tc_splitk(s.XT, Mpad, s.YT, Mpad, dW, K, N, K, Mpad, st)) return 1;
+    static const bool transposed_copies = []() {  // CSE_WGRAD_TRANSPOSE=1: the first version (A/B aid)
+      const char* e = getenv("CSE_WGRAD_TRANSPOSE");
+      return e != nullptr && e[0] == '1';
+    }();
+    if (!transposed_copies) {
+      // dW[N,K] += dC^T A straight from the row-major bf16 dC [M,N] and A [M,K]: MN-major UMMA operands, the token
+      // dimension split over the CTA pairs, TMA reduce-add into dW
+      if (dA == nullptr) {
+        if (launch_f32_to_bf16(dC, s.dC16, (size_t)M * N, st)) return 1;
+      }
+      const bf16* A16 = (const bf16*)A;
+      int lda16 = lda;
+      if (!a_is_bf16) {  // (only the stack's first linear sees an fp32 input)
+        CSE_REQUIRE(lda == K, "linear_bwd_tc: an fp32 A must be contiguous (lda=%d K=%d)", lda, K);
+        if (launch_f32_to_bf16((const float*)A, s.YT, (size_t)M * K, st)) return 1;
+        A16 = s.YT;
+        lda16 = K;
+      }
+      if (launch_gemm_tc_wgrad(s.dC16, N, A16, lda16, dW, K, N, K, M, st)) return 1;
+    } else {
+      if (launch_transpose_cast(dC, 0, N, M, N, Mpad, s.XT, st)) return 1;     // (dC^T) [N, Mpad]
+      if (launch_transpose_cast(A, a_is_bf16, lda, M, K, Mpad, s.YT, st)) return 1;  // (A^T) [K, Mpad]
+      // dW[N,K] += XT YT^T : in-place accumulation through the TMA reduce-add epilogue, the token dimension split
+      // over the CTA pairs (2-8 output tiles alone would leave 140 SMs idle)
+      if (launch_gemm_tc_splitk(s.XT, Mpad, s.YT, Mpad, dW, K, N, K, Mpad, st)) return 1;
+    }
   }
   return 0;
 }
@@ -230,10 +253,14 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
   // ---- attention sub-block ----
   if (cse_linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, dR, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
-  if (launch_bf16_to_f32(w.QKV, w.QKV32, (size_t)M * 3 * kN, st)) return 1;
-  if (launch_bf16_to_f32(w.AO, w.AO32, (size_t)M * kN, st)) return 1;
   float* dQKV = w.dBig;  // [M,768] fp32
-  if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
+  if (n <= 256) {  // tensor-core attention backward straight from the bf16 recompute (attention_bwd_mma.cu)
+    if (launch_attention_bwd_bf16(w.QKV, w.AO, w.dH, nseq, n, dQKV, st)) return 1;
+  } else {         // longer sequences (inter stack beyond ~30 s of audio): the fp32 kernel
+    if (launch_bf16_to_f32(w.QKV, w.QKV32, (size_t)M * 3 * kN, st)) return 1;
+    if (launch_bf16_to_f32(w.AO, w.AO32, (size_t)M * kN, st)) return 1;
+    if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
+  }
   if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
   if (cse_linear_bwd_tc(w.H, 1, kN, p->in_proj_w, dQKV, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;

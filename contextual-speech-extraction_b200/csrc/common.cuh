@@ -217,8 +217,12 @@ int launch_gemm_simt(const float* A, int lda, const float* W, const float* bias,
 int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, float bias_scale,
                    const float* residual, void* C, int ldc, int M, int N, int K, int relu,
                    int out_fp32, cudaStream_t st);
+int launch_attention_bwd_bf16(const bf16* qkv, const bf16* out, const float* d_out, int nseq, int n, float* d_qkv,
+                              cudaStream_t st);  // tensor-core attention backward, n <= 256
 int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const float* bias, float* R, const float* gamma,
                                const float* beta, float eps, bf16* H, int M, int K, cudaStream_t st);
+int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* C, int ldc, int M, int N, int T,
+                         cudaStream_t st);  // C (fp32) += X^T Y over the T tokens (MN-major operands, split over the CTA pairs)
 int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float* C, int ldc, int M, int N, int K,
                           cudaStream_t st);  // C (fp32) += A W^T, K split over the CTA pairs (wgrad)
 // gemm_ln_tc.cu: C(bf16) = act(LN(R) W^T + bias), K = 256

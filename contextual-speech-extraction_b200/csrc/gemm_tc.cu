@@ -77,6 +77,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return make_desc(smem_addr, 1024, kLayoutSw128);
 }
+// MN-major SWIZZLE_128B operand: atoms of 8 k-rows x 64 elements (128 B); SBO = 1024 B between 8-k groups, LBO =
+// 8192 B between 64-element blocks along M / N (one [64 k x 64 mn] TMA box each)
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)kLayoutSw128 << 61;
+  return d;
+}
 // kind::f16, A/B = bf16 K-major, D = fp32
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return tc::make_idesc_bf16(M, N, 0, 0); }
 
@@ -127,7 +138,12 @@ struct LnEpilogue {
   float eps;
 };
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false>
+// MNM (wgrad): BOTH operands are "MN-major" — C[M,N] += X^T Y for row-major X [T,M], Y [T,N] contracted over their
+// slow dimension T (tokens).  TMA brings [64 tokens x 64 features] SWIZZLE_128B boxes (64 lines of 128 B: exactly
+// the canonical MN-major atom stack, 8 token-rows per atom), two per 128 output rows / four per 256 output columns;
+// descriptors: SBO = 1024 B between 8-token groups, LBO = 8192 B between 64-feature blocks; a K = 16 step advances
+// two atoms (2048 B).  No transposed copies of the operands exist (they were 6 ms of a 28.6 ms training step).
+template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false, bool MNM = false>
 __global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES, LNE>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
@@ -136,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
   static_assert(!LNE || (BN == 256 && OUT_F32 && !PAIR && !ARES && Cfg::kEpiWarps == 8),
                 "the LayerNorm epilogue is built on the 256-wide fp32 per-CTA variant");
+  static_assert(!MNM || (OUT_F32 && !PAIR && !ARES && !LNE), "MN-major operands: fp32 per-CTA variant only");
   pdl_launch_dependents();
   static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
@@ -251,6 +268,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d_pair(sA + stage * Cfg::kABytes, &tmA, lead_full, kb * kTK, m0);
             tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, lead_full, kb * kTK, n0 + cta_rank * (BN / 2));
           }
+        } else if constexpr (MNM) {
+          if (lane == 0) {
+            mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
+            mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+            // boxes [64 tokens x 64 features]: coordinates (feature, token)
+#pragma unroll
+            for (int i = 0; i < kTM / 64; ++i)
+              tma_load_2d(sA + stage * Cfg::kABytes + i * 8192, &tmA, bar_full + 8 * stage, m0 + 64 * i, kb * kTK);
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) {  // this CTA's half of the 64-feature blocks -> both CTAs
+              const int blk = cta_rank * (BN / 128) + i;
+              tma_load_2d_mcast(sB + stage * Cfg::kBBytes + blk * 8192, &tmB, bar_full + 8 * stage, n0 + 64 * blk,
+                                kb * kTK, (uint16_t)3);
+            }
+          }
         } else if (lane == 0) {
           mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
           mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
@@ -268,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
     // PAIR: only the leader CTA issues; each UMMA is 256 x BN x 16 across both SMs (A rows and the
     // weight halves come from the same shared-memory offsets in both CTAs, D lands in both TMEMs).
-    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
+    constexpr uint32_t idesc = MNM ? tc::make_idesc_bf16(kTM, BN, 1, 1) : make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
     uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, seg = 0;
     for (int pt = t_begin; pt < t_end && (!PAIR || cta_rank == 0); pt += t_step) {
       const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
@@ -287,8 +319,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (new_rows) mbar_wait_spin(bar_afull + 8 * kb, seg & 1u, 6);
           mbar_wait_spin(bar_full + 8 * stage, phase, 3);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
+          const uint64_t adesc = MNM ? make_mnmajor_sw128_desc(sA + stage * Cfg::kABytes)
+                                     : make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
+          const uint64_t bdesc = MNM ? make_mnmajor_sw128_desc(sB + stage * Cfg::kBBytes)
+                                     : make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
+          if constexpr (MNM) {
+#pragma unroll
+            for (int k = 0; k < kTK / kUmmaK; ++k)  // 16 tokens = two 8-token atoms = 2048 B: +128 in the (addr>>4) field
+              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+          } else
 #pragma unroll
           for (int k = 0; k < kTK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
@@ -651,14 +690,14 @@ int sm_count() {  // of the CURRENT device (cached per ordinal)
   return n;
 }
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false>
+template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false, bool MNM = false>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
                           int N, int K, int relu, cudaStream_t st, int ksplit = 1, LnEpilogue ln = LnEpilogue{}) {
   using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE, MNM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
@@ -670,7 +709,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
+  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE, MNM>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
                                       accumulate, C, ldc, M, N, K, relu, ksplit, ln);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
@@ -750,6 +789,37 @@ int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const floa
   if (get_tensor_map(W, (uint64_t)kN, (uint64_t)K, (uint64_t)K, 128, kTK, 2, &tmB)) return 1;  // half tile per CTA
   LnEpilogue ln{R, gamma, beta, H, eps};
   return launch_tc_impl<256, true, false, false, true>(tmA, tmB, tmA /*unused*/, bias, 1.f, 0, R, kN, M, kN, K, 0, st, 1, ln);
+}
+
+// C[M,N] (fp32) += X^T Y for row-major bf16 X [T, M] (ldx), Y [T, N] (ldy), contracted over the T tokens and split
+// over the CTA pairs: the weight gradient dW = dC^T A straight from the row-major dC and A (MN-major operands).
+int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* C, int ldc, int M, int N, int T,
+                         cudaStream_t st) {
+  if (M <= 0 || T <= 0) return 0;
+  if (M % 128 != 0 || N % 128 != 0 || ldx % 8 != 0 || ldy % 8 != 0 || ldc % 8 != 0) {
+    set_error("gemm_tc_wgrad: need M %% 128 == 0, N %% 128 == 0, ldx/ldy/ldc %% 8 == 0 (M=%d N=%d)", M, N);
+    return 1;
+  }
+  if (((uintptr_t)X | (uintptr_t)Y | (uintptr_t)C) & 15) {
+    set_error("gemm_tc_wgrad: operands must be 16-byte aligned");
+    return 1;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmX, tmY, tmC;
+  if (get_tensor_map(X, (uint64_t)T, (uint64_t)M, (uint64_t)ldx, 64, 64, 2, &tmX)) return 1;  // [64 tokens x 64 features]
+  if (get_tensor_map(Y, (uint64_t)T, (uint64_t)N, (uint64_t)ldy, 64, 64, 2, &tmY)) return 1;
+  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CSE_EPI_ROW_BYTES / 4, 4, &tmC)) return 1;
+  const int Tk = (int)align_up((size_t)T, kTK);     // the token tail of the last k-block reads as zeros (TMA)
+  const int num_kb = Tk / kTK;
+  const int tiles = ceil_div(ceil_div(M, kTM), 2) * (N / BN);
+  int want = (sm_count() / 2) / tiles;
+  if (want > num_kb / 4) want = num_kb / 4;
+  if (want < 1) want = 1;
+  const int kb_per = ceil_div(num_kb, want);
+  const int ksplit = ceil_div(num_kb, kb_per);
+  return BN == 256
+             ? launch_tc_impl<256, true, false, false, false, true>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit)
+             : launch_tc_impl<128, true, false, false, false, true>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit);
 }
 
 // C[M,N] (fp32) += A[M,K] W[N,K]^T with the K dimension split over CTAs: the weight-gradient shape (M, N = a layer's

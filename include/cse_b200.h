@@ -360,6 +360,13 @@ CSE_API int cse_layernorm_bwd(const float* x, const float* g, const float* dy, i
 CSE_API int cse_attention_bwd(const float* qkv, const float* out, const float* d_out, int nseq, int n,
                               float* d_qkv, void* stream);
 
+/* The same gradient on the tensor cores (mma.sync bf16, fp32 softmax algebra and accumulation), performance mode:
+ * qkv [M,768] and out [M,256] are the bf16 tensors of the autocast forward, d_out [M,256] and d_qkv [M,768] fp32.
+ * n <= 256.  Used by cse_layer_bwd_bf16; P and dS are rounded to bf16 for their second contraction, as autocast
+ * does (train_ContSep.py:383). */
+CSE_API int cse_attention_bwd_bf16(const void* qkv_bf16, const void* out_bf16, const float* d_out, int nseq, int n,
+                                   float* d_qkv, void* stream);
+
 /* Gradient buffers of one transformer layer (same shapes as cse_layer_params' fp32 members). */
 typedef struct {
   float* in_proj_w;

@@ -1,12 +1,10 @@
-"""GPU, EXPERIMENTAL: nn.Linear backward on the tcgen05 GEMM (csrc/backward_tc.cu).
-
-Written after the round's GPU budget was spent: the kernel composition has been compiled and
-argument-checked but never run on hardware, so this file is skipped unless CSE_EXPERIMENTAL=1 — it is the
-first thing to run next round.  Tolerance: bf16 operand rounding (2^-9 relative per element) against the
-fp64 closed form, i.e. ~4e-3 relative L2 for these reduction lengths.
+"""GPU: the performance-mode (bf16 tensor-core) backward — nn.Linear dgrad / wgrad on the tcgen05 GEMM
+(csrc/backward_tc.cu, split-K wgrad), the mma.sync attention backward (csrc/attention_bwd_mma.cu) and one whole
+transformer layer (cse_layer_bwd_bf16), i.e. what `loss.backward()` runs under torch.autocast
+(train_ContSep.py:383-400).  Tolerance: bf16 operand rounding (2^-9 relative per element) against the fp64 closed
+forms, i.e. ~4e-3 relative L2 for these reduction lengths.
 """
 import ctypes as C
-import os
 
 import pytest
 import torch
@@ -16,9 +14,7 @@ from cse_b200 import _lib
 from helpers import rel_l2
 from oracle import backward_oracle as BO
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CSE_EXPERIMENTAL") != "1",
-                                 reason="not yet run on hardware; set CSE_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda:0"
 
 
@@ -46,6 +42,32 @@ def test_linear_backward_tensor_core(M, N, K, a_bf16):
     _lib.call("cse_linear_bwd_tc", _lib.ptr(ad), int(a_bf16), K, _lib.ptr(wd), _lib.ptr(dcd), M, N, K, None,
               1, K, _lib.ptr(dw), None, _lib.ptr(ws), nbytes, st)            # dW accumulates
     assert rel_l2(dw.cpu(), 2 * dw_ref) < 6e-3
+
+
+@pytest.mark.parametrize("nseq,n", [(3, 35), (2, 251), (5, 1), (7, 16), (4, 64), (3, 65), (2, 132), (1, 256), (68, 251),
+                                    (500, 35)])
+def test_attention_backward_tensor_core(nseq, n):
+    """cse_attention_bwd_bf16 (mma.sync, both orientations) against the fp64 closed form evaluated on the SAME bf16
+    q/k/v; its `out` input is our own bf16 forward.  Per-matrix relative L2 <= 1.5e-2 (P, dS and dO are rounded to
+    bf16 for the contractions)."""
+    qkv = (_rand(nseq, n, 768, seed=9) * 1.2).to(torch.bfloat16)
+    do = _rand(nseq, n, 256, seed=10)
+    o_ref, dqkv_ref = BO.manual_attention_bwd(qkv.double(), do.double())
+    qd, dod = qkv.to(DEV), do.to(DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.empty(nseq * n, 256, dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_attention_fwd", _lib.ptr(qd), nseq, n, _lib.BF16, _lib.ptr(out), st)
+    assert rel_l2(out.float().cpu().view(nseq, n, 256), o_ref) < 1e-2
+    dqkv = torch.full((nseq, n, 768), float("nan"), device=DEV)
+    _lib.call("cse_attention_bwd_bf16", _lib.ptr(qd), _lib.ptr(out), _lib.ptr(dod), nseq, n, _lib.ptr(dqkv), st)
+    assert torch.isfinite(dqkv).all()
+    for name, sl in (("dq", slice(0, 256)), ("dk", slice(256, 512)), ("dv", slice(512, 768))):
+        got, ref = dqkv.cpu()[..., sl].double(), dqkv_ref[..., sl]
+        # n == 1: softmax of a single score is constant, dq = dk = 0 — here up to the bf16 rounding of dP - D, which is
+        # relative to dv: the floor is a fraction of the whole gradient's norm
+        assert (got - ref).norm() <= 1.5e-2 * max(ref.norm().item(), 0.5 * dqkv_ref.norm().item()), name
+    with pytest.raises(_lib.CseError):
+        _lib.call("cse_attention_bwd_bf16", _lib.ptr(qd), _lib.ptr(out), _lib.ptr(dod), 1, 300, _lib.ptr(dqkv), st)
 
 
 @pytest.mark.parametrize("nseq,n", [(4, 36), (3, 251)])
