@@ -72,9 +72,22 @@ def _workspace(nseq, n, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
-def layer_forward(params, R, nseq, n, experimental_bf16=False):
+def _zero_grads(params):
+    """Gradient buffers of one layer as views of ONE zero-filled allocation (one fill launch instead of twelve)."""
+    sizes = [params[key].numel() for _, key in LAYER_KEYS]
+    offs, total = [], 0
+    for sz in sizes:                      # every view 16-byte aligned (float4 / TMA accesses in the kernels)
+        offs.append(total)
+        total += (sz + 3) // 4 * 4
+    ref = params[LAYER_KEYS[0][1]]
+    flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+    return {key: flat[o:o + sz].view(params[key].shape) for (_, key), o, sz in zip(LAYER_KEYS, offs, sizes)}
+
+
+def layer_forward(params, R, nseq, n, experimental_bf16=False, packs_out=None):
     """TransformerEncoderLayer.forward on the fp32 residual stream R [nseq*n, 256]; returns a new tensor.
-    fp32 arithmetic unless experimental_bf16 (the bench path's tensor-core launch sequence, one layer)."""
+    fp32 arithmetic unless experimental_bf16 (the bench path's tensor-core launch sequence, one layer).
+    packs_out: list that receives the bf16 weight copies, for the backward pass of the same step to reuse."""
     _check(R, "R")
     if R.shape != (nseq * n, _lib.N):
         raise _lib.CseError(f"R has shape {tuple(R.shape)}, expected {(nseq * n, _lib.N)}")
@@ -84,26 +97,32 @@ def layer_forward(params, R, nseq, n, experimental_bf16=False):
     packs = _bf16_packs(params, lp) if experimental_bf16 else None
     _lib.call("cse_layer_fwd", C.byref(lp), _lib.ptr(out), nseq, n, _lib.BF16 if experimental_bf16 else _lib.FP32,
               _lib.ptr(ws), nbytes, C.c_void_p(current_stream(R.device)))
+    if packs_out is not None and packs is not None:
+        packs_out.append(packs)
     del packs
     return out
 
 
-def layer_backward(params, R_in, dR_out, nseq, n, grads=None, experimental_bf16=False):
+def layer_backward(params, R_in, dR_out, nseq, n, grads=None, experimental_bf16=False, packs=None):
     """Gradient of layer_forward: returns (dR_in, grads) with grads keyed like `params`.
     `grads` may carry existing buffers to accumulate into (autograd .grad semantics).
 
-    experimental_bf16: route to cse_layer_bwd_bf16 (tensor-core recompute / dgrad / wgrad) — compiled but not
-    yet run on hardware (csrc/backward_tc.cu); nothing on the default path sets it."""
+    experimental_bf16: route to cse_layer_bwd_bf16 (tensor-core recompute / dgrad / wgrad / attention backward:
+    the autocast training path)."""
     _check(R_in, "R_in")
     _check(dR_out, "dR_out")
     if grads is None:
-        grads = {key: torch.zeros_like(params[key]) for _, key in LAYER_KEYS}
+        grads = _zero_grads(params)
     dR = dR_out.clone()
     lp = _layer_struct(params, _lib.LayerParams)
     lg = _layer_struct(grads, _lib.LayerGrads)
     st = C.c_void_p(current_stream(R_in.device))
     if experimental_bf16:
-        packs = _bf16_packs(params, lp)  # noqa: F841  (kept alive until the call below is enqueued)
+        if packs is None:                # (kept alive until the call below is enqueued)
+            packs = _bf16_packs(params, lp)
+        else:                            # the forward's bf16 weight copies: the weights do not change within a step
+            for field, _ in LAYER_KEYS[:8:2]:
+                setattr(lp, field + "_bf16", C.c_void_p(packs[field].data_ptr()))
         nbytes = _lib.load().cse_layer_bwd_bf16_workspace_bytes(nseq, n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=R_in.device)
         _lib.call("cse_layer_bwd_bf16", C.byref(lp), C.byref(lg), _lib.ptr(R_in), _lib.ptr(dR), nseq, n,
@@ -123,14 +142,19 @@ class _LayerFn(torch.autograd.Function):
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
         ctx.save_for_backward(R, *weights)
         ctx.shape = (nseq, n, bool(bf16))
-        return layer_forward(params, R.contiguous(), nseq, n, experimental_bf16=bool(bf16))
+        ctx.packs = []
+        ctx.versions = [w._version for w in weights]
+        return layer_forward(params, R.contiguous(), nseq, n, experimental_bf16=bool(bf16), packs_out=ctx.packs)
 
     @staticmethod
     def backward(ctx, dR_out):
         R, *weights = ctx.saved_tensors
         nseq, n, bf16 = ctx.shape
         params = {key: w for (_, key), w in zip(LAYER_KEYS, weights)}
-        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n, experimental_bf16=bf16)
+        same = all(w._version == v for w, v in zip(weights, ctx.versions))   # untouched since the forward pass
+        packs = ctx.packs[0] if (ctx.packs and same) else None
+        dR, grads = layer_backward(params, R.contiguous(), dR_out.contiguous(), nseq, n, experimental_bf16=bf16,
+                                   packs=packs)
         return (dR, None, None, None) + tuple(grads[key] for _, key in LAYER_KEYS)
 
 

@@ -80,9 +80,10 @@ size_t cse_linear_bwd_tc_scratch_bytes(int M, int N, int K) {
   return carve_tc_bwd(nullptr, (size_t)M, (size_t)N, (size_t)K).total;
 }
 
-int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const float* dC, int M, int N,
-                      int K, void* dA, int dA_fp32, int ldda, float* dW, float* dbias, void* scratch,
-                      size_t scratch_bytes, void* stream) {
+// W16: optional bf16 copy of W [N,K] (the forward's packed weights); NULL = cast W here
+static int linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const bf16* W16, const float* dC,
+                         int M, int N, int K, void* dA, int dA_fp32, int ldda, float* dW, float* dbias,
+                         void* scratch, size_t scratch_bytes, void* stream) {
   CSE_REQUIRE(A && W && dC && scratch && M > 0, "linear_bwd_tc: bad argument");
   CSE_REQUIRE(N % 128 == 0 && K % 128 == 0, "linear_bwd_tc: N and K must be multiples of 128 (N=%d K=%d)", N, K);
   CSE_REQUIRE(dbias == nullptr || N % 256 == 0, "linear_bwd_tc: bias gradient needs N %% 256 == 0 (N=%d)", N);
@@ -91,26 +92,36 @@ int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, con
   CSE_REQUIRE(scratch_bytes >= s.total, "linear_bwd_tc: scratch too small (%zu < %zu bytes)", scratch_bytes, s.total);
   cudaStream_t st = (cudaStream_t)stream;
   const int Mpad = (int)align_up((size_t)M, 64);
-  if (dbias != nullptr) {
-    if (launch_colsum(dC, N, M, N, dbias, st)) return 1;
+  static const bool transposed_copies = []() {  // CSE_WGRAD_TRANSPOSE=1: the first version, which fed the forward
+    const char* e = getenv("CSE_WGRAD_TRANSPOSE");  // (K-major) GEMM transposed bf16 copies of W, dC and A (A/B aid)
+    return e != nullptr && e[0] == '1';
+  }();
+  bool have_dc16 = false;  // the bf16 copy of dC feeds both the dgrad and the wgrad
+  if (dbias != nullptr) {  // bias gradient and the bf16 copy in one pass over dC
+    if (launch_colsum_cast(dC, M, N, dbias, s.dC16, st)) return 1;
+    have_dc16 = true;
   }
   if (dA != nullptr) {
-    if (launch_f32_to_bf16(dC, s.dC16, (size_t)M * N, st)) return 1;
-    if (launch_transpose(W, N, K, s.WT32, st)) return 1;                     // W^T [K,N] fp32
-    if (launch_f32_to_bf16(s.WT32, s.WT16, (size_t)N * K, st)) return 1;
-    if (launch_gemm_tc(s.dC16, N, s.WT16, nullptr, 0.f, nullptr, dA, ldda, M, K, N, 0, dA_fp32 ? 1 : 0, st)) return 1;
+    if (!have_dc16 && launch_f32_to_bf16(dC, s.dC16, (size_t)M * N, st)) return 1;
+    have_dc16 = true;
+    if (!transposed_copies) {
+      // dA = dC W with W as stored ([N,K] row-major = the MN-major B operand): no transposed weight copy
+      if (W16 == nullptr) {
+        if (launch_f32_to_bf16(W, s.WT16, (size_t)N * K, st)) return 1;
+        W16 = s.WT16;
+      }
+      if (launch_gemm_tc_dgrad(s.dC16, N, W16, K, dA, ldda, dA_fp32 ? 1 : 0, M, K, N, st)) return 1;
+    } else {
+      if (launch_transpose(W, N, K, s.WT32, st)) return 1;                     // W^T [K,N] fp32
+      if (launch_f32_to_bf16(s.WT32, s.WT16, (size_t)N * K, st)) return 1;
+      if (launch_gemm_tc(s.dC16, N, s.WT16, nullptr, 0.f, nullptr, dA, ldda, M, K, N, 0, dA_fp32 ? 1 : 0, st)) return 1;
+    }
   }
   if (dW != nullptr) {
-    static const bool transposed_copies = []() {  // CSE_WGRAD_TRANSPOSE=1: the first version (A/B aid)
-      const char* e = getenv("CSE_WGRAD_TRANSPOSE");
-      return e != nullptr && e[0] == '1';
-    }();
     if (!transposed_copies) {
       // dW[N,K] += dC^T A straight from the row-major bf16 dC [M,N] and A [M,K]: MN-major UMMA operands, the token
       // dimension split over the CTA pairs, TMA reduce-add into dW
-      if (dA == nullptr) {
-        if (launch_f32_to_bf16(dC, s.dC16, (size_t)M * N, st)) return 1;
-      }
+      if (!have_dc16 && launch_f32_to_bf16(dC, s.dC16, (size_t)M * N, st)) return 1;
       const bf16* A16 = (const bf16*)A;
       int lda16 = lda;
       if (!a_is_bf16) {  // (only the stack's first linear sees an fp32 input)
@@ -129,6 +140,13 @@ int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, con
     }
   }
   return 0;
+}
+
+int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const float* dC, int M, int N,
+                      int K, void* dA, int dA_fp32, int ldda, float* dW, float* dbias, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+  return linear_bwd_tc(A, a_is_bf16, lda, W, nullptr, dC, M, N, K, dA, dA_fp32, ldda, dW, dbias, scratch, scratch_bytes,
+                       stream);
 }
 
 }  // extern "C"
@@ -243,15 +261,15 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
   if (launch_gemm_tc(w.H, kN, (const bf16*)p->ffn1_w_bf16, p->ffn1_b, 1.f, nullptr, w.F1, kFfn, M, kFfn, kN, 1, 0, st)) return 1;
 
   // ---- FFN sub-block ----
-  if (cse_linear_bwd_tc(w.F1, 1, kFfn, p->ffn2_w, dR, M, kN, kFfn, w.dBig, 1, kFfn, g->ffn2_w, g->ffn2_b, w.lin,
+  if (linear_bwd_tc(w.F1, 1, kFfn, p->ffn2_w, (const bf16*)p->ffn2_w_bf16, dR, M, kN, kFfn, w.dBig, 1, kFfn, g->ffn2_w, g->ffn2_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   if (launch_relu_bwd_mixed(w.F1, w.dBig, (size_t)M * kFfn, st)) return 1;
-  if (cse_linear_bwd_tc(w.H, 1, kN, p->ffn1_w, w.dBig, M, kFfn, kN, w.dH, 1, kN, g->ffn1_w, g->ffn1_b, w.lin,
+  if (linear_bwd_tc(w.H, 1, kN, p->ffn1_w, (const bf16*)p->ffn1_w_bf16, w.dBig, M, kFfn, kN, w.dH, 1, kN, g->ffn1_w, g->ffn1_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   if (launch_layernorm_bwd(w.Rmid, p->ln2_g, w.dH, M, 1e-6f, dR, 1, g->ln2_g, g->ln2_b, st)) return 1;
 
   // ---- attention sub-block ----
-  if (cse_linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, dR, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
+  if (linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, (const bf16*)p->out_proj_w_bf16, dR, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   float* dQKV = w.dBig;  // [M,768] fp32
   if (n <= 256) {  // tensor-core attention backward straight from the bf16 recompute (attention_bwd_mma.cu)
@@ -262,7 +280,7 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
     if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
   }
   if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
-  if (cse_linear_bwd_tc(w.H, 1, kN, p->in_proj_w, dQKV, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
+  if (linear_bwd_tc(w.H, 1, kN, p->in_proj_w, (const bf16*)p->in_proj_w_bf16, dQKV, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   return launch_layernorm_bwd(R_in, p->ln1_g, w.dH, M, 1e-6f, dR, 1, g->ln1_g, g->ln1_b, st);
 }

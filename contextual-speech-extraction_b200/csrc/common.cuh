@@ -221,6 +221,8 @@ int launch_attention_bwd_bf16(const bf16* qkv, const bf16* out, const float* d_o
                               cudaStream_t st);  // tensor-core attention backward, n <= 256
 int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const float* bias, float* R, const float* gamma,
                                const float* beta, float eps, bf16* H, int M, int K, cudaStream_t st);
+int launch_gemm_tc_dgrad(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int out_fp32, int M, int N,
+                         int K, cudaStream_t st);  // C = A W for the row-major W [K,N] (B operand MN-major)
 int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* C, int ldc, int M, int N, int T,
                          cudaStream_t st);  // C (fp32) += X^T Y over the T tokens (MN-major operands, split over the CTA pairs)
 int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float* C, int ldc, int M, int N, int K,
@@ -266,6 +268,7 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
 int launch_wgrad(const float* X, int ldx, const float* Y, int ldy, int M, int N1, int N2, float* dW,
                  cudaStream_t st);
 int launch_colsum(const float* dC, int ld, int M, int N, float* db, cudaStream_t st);
+int launch_colsum_cast(const float* dC, int M, int N, float* db, bf16* dC16, cudaStream_t st);  // + bf16 copy of dC
 int launch_relu_bwd(const float* F, float* d, size_t n, cudaStream_t st);
 int launch_layernorm_bwd(const float* x, const float* g, const float* dy, int M, float eps, float* dx,
                          int accumulate, float* dg, float* db, cudaStream_t st);

@@ -138,12 +138,14 @@ struct LnEpilogue {
   float eps;
 };
 
-// MNM (wgrad): BOTH operands are "MN-major" — C[M,N] += X^T Y for row-major X [T,M], Y [T,N] contracted over their
+// MNM = 2 (dgrad): only the B operand is MN-major — C[M,N] = A[M,K] W[K,N] for the row-major weight W as stored
+// ([out, in] = [K, N]: dA = dC W needs no transposed weight copy); A stays K-major.
+// MNM = 1 (wgrad): BOTH operands are "MN-major" — C[M,N] += X^T Y for row-major X [T,M], Y [T,N] contracted over their
 // slow dimension T (tokens).  TMA brings [64 tokens x 64 features] SWIZZLE_128B boxes (64 lines of 128 B: exactly
 // the canonical MN-major atom stack, 8 token-rows per atom), two per 128 output rows / four per 256 output columns;
 // descriptors: SBO = 1024 B between 8-token groups, LBO = 8192 B between 64-feature blocks; a K = 16 step advances
 // two atoms (2048 B).  No transposed copies of the operands exist (they were 6 ms of a 28.6 ms training step).
-template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false, bool MNM = false>
+template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false, int MNM = 0>
 __global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES, LNE>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
@@ -152,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
   static_assert(!LNE || (BN == 256 && OUT_F32 && !PAIR && !ARES && Cfg::kEpiWarps == 8),
                 "the LayerNorm epilogue is built on the 256-wide fp32 per-CTA variant");
-  static_assert(!MNM || (OUT_F32 && !PAIR && !ARES && !LNE), "MN-major operands: fp32 per-CTA variant only");
+  static_assert(MNM == 0 || (!PAIR && !ARES && !LNE), "MN-major operands: per-CTA variant only");
   pdl_launch_dependents();
   static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
@@ -268,14 +270,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d_pair(sA + stage * Cfg::kABytes, &tmA, lead_full, kb * kTK, m0);
             tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, lead_full, kb * kTK, n0 + cta_rank * (BN / 2));
           }
-        } else if constexpr (MNM) {
+        } else if constexpr (MNM != 0) {
           if (lane == 0) {
             mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
             mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
-            // boxes [64 tokens x 64 features]: coordinates (feature, token)
+            // MN-major boxes [64 k x 64 m/n]: coordinates (m/n, k)
+            if constexpr (MNM == 1) {
 #pragma unroll
-            for (int i = 0; i < kTM / 64; ++i)
-              tma_load_2d(sA + stage * Cfg::kABytes + i * 8192, &tmA, bar_full + 8 * stage, m0 + 64 * i, kb * kTK);
+              for (int i = 0; i < kTM / 64; ++i)
+                tma_load_2d(sA + stage * Cfg::kABytes + i * 8192, &tmA, bar_full + 8 * stage, m0 + 64 * i, kb * kTK);
+            } else {
+              tma_load_2d(sA + stage * Cfg::kABytes, &tmA, bar_full + 8 * stage, kb * kTK, m0);
+            }
 #pragma unroll
             for (int i = 0; i < BN / 128; ++i) {  // this CTA's half of the 64-feature blocks -> both CTAs
               const int blk = cta_rank * (BN / 128) + i;
@@ -300,7 +306,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
     // PAIR: only the leader CTA issues; each UMMA is 256 x BN x 16 across both SMs (A rows and the
     // weight halves come from the same shared-memory offsets in both CTAs, D lands in both TMEMs).
-    constexpr uint32_t idesc = MNM ? tc::make_idesc_bf16(kTM, BN, 1, 1) : make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
+    constexpr uint32_t idesc = MNM != 0 ? tc::make_idesc_bf16(kTM, BN, MNM == 1 ? 1 : 0, 1)
+                                        : make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
     uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, seg = 0;
     for (int pt = t_begin; pt < t_end && (!PAIR || cta_rank == 0); pt += t_step) {
       const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
@@ -319,14 +326,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (new_rows) mbar_wait_spin(bar_afull + 8 * kb, seg & 1u, 6);
           mbar_wait_spin(bar_full + 8 * stage, phase, 3);
           tc_fence_after();
-          const uint64_t adesc = MNM ? make_mnmajor_sw128_desc(sA + stage * Cfg::kABytes)
-                                     : make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
-          const uint64_t bdesc = MNM ? make_mnmajor_sw128_desc(sB + stage * Cfg::kBBytes)
-                                     : make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
-          if constexpr (MNM) {
+          const uint64_t adesc = MNM == 1 ? make_mnmajor_sw128_desc(sA + stage * Cfg::kABytes)
+                                          : make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
+          const uint64_t bdesc = MNM != 0 ? make_mnmajor_sw128_desc(sB + stage * Cfg::kBBytes)
+                                          : make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
+          if constexpr (MNM != 0) {
+            // a K = 16 step: MN-major = two 8-k atoms = 2048 B (+128 in the addr>>4 field); K-major = 32 B (+2)
+            constexpr int kAStep = MNM == 1 ? 128 : 2;
 #pragma unroll
-            for (int k = 0; k < kTK / kUmmaK; ++k)  // 16 tokens = two 8-token atoms = 2048 B: +128 in the (addr>>4) field
-              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kTK / kUmmaK; ++k)
+              umma_bf16(d_tmem, adesc + kAStep * k, bdesc + 128 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           } else
 #pragma unroll
           for (int k = 0; k < kTK / kUmmaK; ++k) {
@@ -690,7 +699,7 @@ int sm_count() {  // of the CURRENT device (cached per ordinal)
   return n;
 }
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false, bool MNM = false>
+template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false, int MNM = 0>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
                           int N, int K, int relu, cudaStream_t st, int ksplit = 1, LnEpilogue ln = LnEpilogue{}) {
@@ -791,6 +800,33 @@ int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const floa
   return launch_tc_impl<256, true, false, false, true>(tmA, tmB, tmA /*unused*/, bias, 1.f, 0, R, kN, M, kN, K, 0, st, 1, ln);
 }
 
+// C[M,N] = A[M,K] W[K,N] for the row-major bf16 W [K, N] as nn.Linear stores it ([out, in]): the input gradient
+// dA = dC W without a transposed weight copy (B operand MN-major).  C fp32 or bf16, overwritten.
+int launch_gemm_tc_dgrad(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int out_fp32, int M, int N,
+                         int K, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (K % kTK != 0 || N % 128 != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldc % 8 != 0) {
+    set_error("gemm_tc_dgrad: need K %% 64 == 0, N %% 128 == 0, lda/ldw/ldc %% 8 == 0 (M=%d N=%d K=%d)", M, N, K);
+    return 1;
+  }
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) {
+    set_error("gemm_tc_dgrad: operands must be 16-byte aligned");
+    return 1;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB, tmC;
+  if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
+  if (get_tensor_map(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 64, 64, 2, &tmB)) return 1;  // [64 k x 64 n] boxes
+  if (get_tensor_map(C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CSE_EPI_ROW_BYTES / (out_fp32 ? 4 : 2),
+                     out_fp32 ? 4 : 2, &tmC))
+    return 1;
+  if (BN == 256)
+    return out_fp32 ? launch_tc_impl<256, true, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
+                    : launch_tc_impl<256, false, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
+  return out_fp32 ? launch_tc_impl<128, true, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
+                  : launch_tc_impl<128, false, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
+}
+
 // C[M,N] (fp32) += X^T Y for row-major bf16 X [T, M] (ldx), Y [T, N] (ldy), contracted over the T tokens and split
 // over the CTA pairs: the weight gradient dW = dC^T A straight from the row-major dC and A (MN-major operands).
 int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* C, int ldc, int M, int N, int T,
@@ -818,8 +854,8 @@ int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* 
   const int kb_per = ceil_div(num_kb, want);
   const int ksplit = ceil_div(num_kb, kb_per);
   return BN == 256
-             ? launch_tc_impl<256, true, false, false, false, true>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit)
-             : launch_tc_impl<128, true, false, false, false, true>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit);
+             ? launch_tc_impl<256, true, false, false, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit)
+             : launch_tc_impl<128, true, false, false, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit);
 }
 
 // C[M,N] (fp32) += A[M,K] W[N,K]^T with the K dimension split over CTAs: the weight-gradient shape (M, N = a layer's
