@@ -174,36 +174,35 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   if (m0 < m1) atomicAdd(db + col, (s0 + s1) + (s2 + s3));
 }
 
-// the same pass also writing the bf16 copy of dC the tensor-core dgrad / wgrad consume (one read of dC instead of two)
-__global__ void __launch_bounds__(256) colsum_cast_kernel(const float* __restrict__ dC, int ld, int M,
-                                                          int rows_per_cta, float* __restrict__ db,
+// the same pass also writing the bf16 copy of dC the tensor-core dgrad / wgrad consume (one read of dC instead of
+// two), optionally through a ReLU mask: relu != NULL -> dC[m,n] counts only where relu[m,n] > 0 (the saved bf16
+// activation of Linear -> ReLU: torch's threshold_backward folded into this pass)
+template <bool RELU>
+__global__ void __launch_bounds__(256) colsum_cast_kernel(const float* __restrict__ dC, const bf16* __restrict__ relu,
+                                                          int ld, int M, int rows_per_cta, float* __restrict__ db,
                                                           bf16* __restrict__ dC16) {
   const int col = blockIdx.y * 256 + threadIdx.x;
   const int m0 = blockIdx.x * rows_per_cta;
   const int m1 = min(M, m0 + rows_per_cta);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  auto at = [&](int m) {
+    float v = dC[(size_t)m * ld + col];
+    if (RELU) v = __bfloat162float(relu[(size_t)m * ld + col]) > 0.f ? v : 0.f;
+    dC16[(size_t)m * ld + col] = __float2bfloat16_rn(v);
+    return v;
+  };
   int m = m0;
   for (; m + 3 < m1; m += 4) {
-    const float a = dC[(size_t)m * ld + col], b = dC[(size_t)(m + 1) * ld + col];
-    const float c = dC[(size_t)(m + 2) * ld + col], d = dC[(size_t)(m + 3) * ld + col];
-    dC16[(size_t)m * ld + col] = __float2bfloat16_rn(a);
-    dC16[(size_t)(m + 1) * ld + col] = __float2bfloat16_rn(b);
-    dC16[(size_t)(m + 2) * ld + col] = __float2bfloat16_rn(c);
-    dC16[(size_t)(m + 3) * ld + col] = __float2bfloat16_rn(d);
-    s0 += a;
-    s1 += b;
-    s2 += c;
-    s3 += d;
+    s0 += at(m);
+    s1 += at(m + 1);
+    s2 += at(m + 2);
+    s3 += at(m + 3);
   }
-  for (; m < m1; ++m) {
-    const float a = dC[(size_t)m * ld + col];
-    dC16[(size_t)m * ld + col] = __float2bfloat16_rn(a);
-    s0 += a;
-  }
+  for (; m < m1; ++m) s0 += at(m);
   if (m0 < m1) atomicAdd(db + col, (s0 + s1) + (s2 + s3));
 }
 
-int launch_colsum_cast(const float* dC, int M, int N, float* db, bf16* dC16, cudaStream_t st) {
+int launch_colsum_cast(const float* dC, const bf16* relu, int M, int N, float* db, bf16* dC16, cudaStream_t st) {
   if (N % 256 != 0) {
     set_error("colsum_cast: need N %% 256 == 0 (N=%d)", N);
     return 1;
@@ -213,7 +212,10 @@ int launch_colsum_cast(const float* dC, int M, int N, float* db, bf16* dC16, cud
   int rows_per_cta = ceil_div(M, ctas);
   if (rows_per_cta < 32) rows_per_cta = 32;
   ctas = ceil_div(M, rows_per_cta);
-  colsum_cast_kernel<<<dim3(ctas, N / 256), 256, 0, st>>>(dC, N, M, rows_per_cta, db, dC16);
+  if (relu != nullptr)
+    colsum_cast_kernel<true><<<dim3(ctas, N / 256), 256, 0, st>>>(dC, relu, N, M, rows_per_cta, db, dC16);
+  else
+    colsum_cast_kernel<false><<<dim3(ctas, N / 256), 256, 0, st>>>(dC, nullptr, N, M, rows_per_cta, db, dC16);
   return check_launch("colsum_cast_kernel");
 }
 

@@ -80,10 +80,23 @@ size_t cse_linear_bwd_tc_scratch_bytes(int M, int N, int K) {
   return carve_tc_bwd(nullptr, (size_t)M, (size_t)N, (size_t)K).total;
 }
 
-// W16: optional bf16 copy of W [N,K] (the forward's packed weights); NULL = cast W here
+// CSE_WGRAD_TRANSPOSE=1: the first version, which fed the forward (K-major) GEMM transposed bf16 copies of W, dC and A
+// (A/B aid)
+static bool wgrad_transposed_copies() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_WGRAD_TRANSPOSE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+// W16: optional bf16 copy of W [N,K] (the forward's packed weights); NULL = cast W here.
+// relu: optional saved bf16 output [M,N] of a ReLU that followed this Linear: dC is masked by it on the fly
+// (needs dbias, i.e. the fused bias-gradient / cast pass).
 static int linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const bf16* W16, const float* dC,
-                         int M, int N, int K, void* dA, int dA_fp32, int ldda, float* dW, float* dbias,
-                         void* scratch, size_t scratch_bytes, void* stream) {
+                         const bf16* relu, int M, int N, int K, void* dA, int dA_fp32, int ldda, float* dW,
+                         float* dbias, void* scratch, size_t scratch_bytes, void* stream) {
+  CSE_REQUIRE(relu == nullptr || dbias != nullptr, "linear_bwd_tc: the ReLU mask rides on the bias-gradient pass");
   CSE_REQUIRE(A && W && dC && scratch && M > 0, "linear_bwd_tc: bad argument");
   CSE_REQUIRE(N % 128 == 0 && K % 128 == 0, "linear_bwd_tc: N and K must be multiples of 128 (N=%d K=%d)", N, K);
   CSE_REQUIRE(dbias == nullptr || N % 256 == 0, "linear_bwd_tc: bias gradient needs N %% 256 == 0 (N=%d)", N);
@@ -92,13 +105,11 @@ static int linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, 
   CSE_REQUIRE(scratch_bytes >= s.total, "linear_bwd_tc: scratch too small (%zu < %zu bytes)", scratch_bytes, s.total);
   cudaStream_t st = (cudaStream_t)stream;
   const int Mpad = (int)align_up((size_t)M, 64);
-  static const bool transposed_copies = []() {  // CSE_WGRAD_TRANSPOSE=1: the first version, which fed the forward
-    const char* e = getenv("CSE_WGRAD_TRANSPOSE");  // (K-major) GEMM transposed bf16 copies of W, dC and A (A/B aid)
-    return e != nullptr && e[0] == '1';
-  }();
+  const bool transposed_copies = wgrad_transposed_copies();
+  CSE_REQUIRE(relu == nullptr || !transposed_copies, "linear_bwd_tc: no ReLU mask in the transposed-copies mode");
   bool have_dc16 = false;  // the bf16 copy of dC feeds both the dgrad and the wgrad
   if (dbias != nullptr) {  // bias gradient and the bf16 copy in one pass over dC
-    if (launch_colsum_cast(dC, M, N, dbias, s.dC16, st)) return 1;
+    if (launch_colsum_cast(dC, relu, M, N, dbias, s.dC16, st)) return 1;
     have_dc16 = true;
   }
   if (dA != nullptr) {
@@ -145,7 +156,7 @@ static int linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, 
 int cse_linear_bwd_tc(const void* A, int a_is_bf16, int lda, const float* W, const float* dC, int M, int N,
                       int K, void* dA, int dA_fp32, int ldda, float* dW, float* dbias, void* scratch,
                       size_t scratch_bytes, void* stream) {
-  return linear_bwd_tc(A, a_is_bf16, lda, W, nullptr, dC, M, N, K, dA, dA_fp32, ldda, dW, dbias, scratch, scratch_bytes,
+  return linear_bwd_tc(A, a_is_bf16, lda, W, nullptr, dC, nullptr, M, N, K, dA, dA_fp32, ldda, dW, dbias, scratch, scratch_bytes,
                        stream);
 }
 
@@ -261,15 +272,20 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
   if (launch_gemm_tc(w.H, kN, (const bf16*)p->ffn1_w_bf16, p->ffn1_b, 1.f, nullptr, w.F1, kFfn, M, kFfn, kN, 1, 0, st)) return 1;
 
   // ---- FFN sub-block ----
-  if (linear_bwd_tc(w.F1, 1, kFfn, p->ffn2_w, (const bf16*)p->ffn2_w_bf16, dR, M, kN, kFfn, w.dBig, 1, kFfn, g->ffn2_w, g->ffn2_b, w.lin,
+  if (linear_bwd_tc(w.F1, 1, kFfn, p->ffn2_w, (const bf16*)p->ffn2_w_bf16, dR, nullptr, M, kN, kFfn, w.dBig, 1, kFfn, g->ffn2_w, g->ffn2_b, w.lin,
                         w.lin_bytes, stream)) return 1;
-  if (launch_relu_bwd_mixed(w.F1, w.dBig, (size_t)M * kFfn, st)) return 1;
-  if (linear_bwd_tc(w.H, 1, kN, p->ffn1_w, (const bf16*)p->ffn1_w_bf16, w.dBig, M, kFfn, kN, w.dH, 1, kN, g->ffn1_w, g->ffn1_b, w.lin,
+  // (the ReLU between ffn.0 and ffn.3 is differentiated inside the next call's bias-gradient / cast pass)
+  const bf16* relu_mask = w.F1;
+  if (wgrad_transposed_copies()) {
+    if (launch_relu_bwd_mixed(w.F1, w.dBig, (size_t)M * kFfn, st)) return 1;
+    relu_mask = nullptr;
+  }
+  if (linear_bwd_tc(w.H, 1, kN, p->ffn1_w, (const bf16*)p->ffn1_w_bf16, w.dBig, relu_mask, M, kFfn, kN, w.dH, 1, kN, g->ffn1_w, g->ffn1_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   if (launch_layernorm_bwd(w.Rmid, p->ln2_g, w.dH, M, 1e-6f, dR, 1, g->ln2_g, g->ln2_b, st)) return 1;
 
   // ---- attention sub-block ----
-  if (linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, (const bf16*)p->out_proj_w_bf16, dR, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
+  if (linear_bwd_tc(w.AO, 1, kN, p->out_proj_w, (const bf16*)p->out_proj_w_bf16, dR, nullptr, M, kN, kN, w.dH, 1, kN, g->out_proj_w, g->out_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   float* dQKV = w.dBig;  // [M,768] fp32
   if (n <= 256) {  // tensor-core attention backward straight from the bf16 recompute (attention_bwd_mma.cu)
@@ -280,7 +296,7 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
     if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
   }
   if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
-  if (linear_bwd_tc(w.H, 1, kN, p->in_proj_w, (const bf16*)p->in_proj_w_bf16, dQKV, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
+  if (linear_bwd_tc(w.H, 1, kN, p->in_proj_w, (const bf16*)p->in_proj_w_bf16, dQKV, nullptr, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   return launch_layernorm_bwd(R_in, p->ln1_g, w.dH, M, 1e-6f, dR, 1, g->ln1_g, g->ln1_b, st);
 }

@@ -268,7 +268,8 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
 int launch_wgrad(const float* X, int ldx, const float* Y, int ldy, int M, int N1, int N2, float* dW,
                  cudaStream_t st);
 int launch_colsum(const float* dC, int ld, int M, int N, float* db, cudaStream_t st);
-int launch_colsum_cast(const float* dC, int M, int N, float* db, bf16* dC16, cudaStream_t st);  // + bf16 copy of dC
+int launch_colsum_cast(const float* dC, const bf16* relu, int M, int N, float* db, bf16* dC16,
+                       cudaStream_t st);  // + bf16 copy of dC, optionally through the ReLU mask of the saved activation
 int launch_relu_bwd(const float* F, float* d, size_t n, cudaStream_t st);
 int launch_layernorm_bwd(const float* x, const float* g, const float* dy, int M, float eps, float* dx,
                          int accumulate, float* dg, float* db, cudaStream_t st);
