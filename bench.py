@@ -531,7 +531,15 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     model.precision = None if amp else "fp32"
     net = model
     if world > 1:   # the reference's own wrapper (train_ContExt.py:269-273): bucketed NCCL all-reduce overlapped with backward
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        ddp_kw = {}
+        if args.ddp_bucket_view:
+            ddp_kw["gradient_as_bucket_view"] = True
+        if args.ddp_bucket_mb:
+            ddp_kw["bucket_cap_mb"] = args.ddp_bucket_mb
+        if args.ddp_static_graph:
+            ddp_kw["static_graph"] = True
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                        find_unused_parameters=False, **ddp_kw)
     fused_opt = args.train_optim == "fused"
     if fused_opt:   # clip_grad_norm_ + AdamW(amsgrad) in three launches (cse_optim_step), no host sync on the norm
         from cse_b200.optim import AdamW as FusedAdamW
@@ -646,7 +654,8 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
         ms_ar, _ = timed(allreduce_alone, steps)
         exposed = max(0.0, ms_step - ms_nosync / steps)
         alone = ms_ar / steps
-        comm = {"collective": "NCCL all-reduce of fp32 gradients (stock DistributedDataParallel, 25 MB buckets)",
+        comm = {"collective": "NCCL all-reduce of fp32 gradients (stock DistributedDataParallel"
+                              + (f", {ddp_kw}" if ddp_kw else ", default arguments as train_ContExt.py:269-273: 25 MB buckets") + ")",
                 "allreduce_bytes_per_step": n_params * 4, "step_ms": ms_step, "step_ms_without_allreduce": ms_nosync / steps,
                 "exposed_allreduce_ms": exposed, "allreduce_alone_ms": alone,
                 "overlap_fraction": max(0.0, min(1.0, 1.0 - exposed / alone)) if alone > 0 else None}
@@ -726,6 +735,9 @@ def main():
     ap.add_argument("--train-ragged", action="store_true",
                     help="training leg: DailyTalk-like lengths U(1.5 s, 8 s) right-padded to the batch max instead of fixed --train-seconds")
     ap.add_argument("--no-train", action="store_true", help="forward workload: skip the `train` sub-object")
+    ap.add_argument("--ddp-bucket-view", action="store_true", help="training leg, N > 1: DDP(gradient_as_bucket_view=True) (A/B; the reference uses the defaults)")
+    ap.add_argument("--ddp-bucket-mb", type=int, default=0, help="training leg, N > 1: DDP(bucket_cap_mb=...) (A/B; default 25)")
+    ap.add_argument("--ddp-static-graph", action="store_true", help="training leg, N > 1: DDP(static_graph=True) (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "cse_decimate": (C.c_int, [_v, _v, C.c_int, C.c_longlong, C.c_int, _v, C.c_int, C.c_longlong, _v, _v, _v]),
     "cse_optim_chunk_count": (C.c_longlong, [C.c_int, C.POINTER(C.c_longlong)]),
     "cse_optim_table_fill": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)] + [C.POINTER(_v)] * 5 + [_v, C.c_size_t]),
+    "cse_optim_table_set_grads": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(_v), _v, C.c_size_t]),
     "cse_optim_step": (C.c_int, [_v, C.c_longlong] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int, C.c_float,
                                  C.c_float, C.c_int, C.c_int, _v, _v, _v]),
     "cse_layer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

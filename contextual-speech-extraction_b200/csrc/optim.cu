@@ -224,6 +224,21 @@ int cse_optim_table_fill(int n_tensors, const long long* numel, void* const* par
   return 0;
 }
 
+int cse_optim_table_set_grads(int n_tensors, const long long* numel, void* const* grad, void* host_table,
+                              size_t host_table_bytes) {
+  CSE_REQUIRE(n_tensors > 0 && numel && grad && host_table, "optim_table_set_grads: NULL argument");
+  const long long n_chunks = cse_optim_chunk_count(n_tensors, numel);
+  CSE_REQUIRE(n_chunks > 0 && host_table_bytes >= (size_t)n_chunks * sizeof(OptimChunk),
+              "optim_table_set_grads: table too small");
+  OptimChunk* t = reinterpret_cast<OptimChunk*>(host_table);
+  long long k = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    CSE_REQUIRE(numel[i] == 0 || grad[i], "optim_table_set_grads: tensor %d has a NULL gradient", i);
+    for (long long off = 0; off < numel[i]; off += kOptChunk, ++k) t[k].g = (float*)grad[i] + off;
+  }
+  return 0;
+}
+
 int cse_optim_step(const void* device_table, long long n_chunks, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int amsgrad, float max_norm, int use_scaler, float growth_factor,
                    float backoff_factor, int growth_interval, int write_back_grads, void* state, float* partial,

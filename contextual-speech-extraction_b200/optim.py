@@ -47,7 +47,7 @@ class AdamW(torch.optim.Optimizer):
         if d is None:
             st = torch.zeros(_STATE_FLOATS, dtype=torch.float32, device=device)
             st[2] = self._scaler[0]
-            d = self._dev[gi] = dict(state=st, key=None, table=None, n_chunks=0, partial=None, keep=None)
+            d = self._dev[gi] = dict(state=st, key=None, gptrs=None, table=None, n_chunks=0, partial=None)
         return d
 
     def _moments(self, p, amsgrad):
@@ -59,24 +59,54 @@ class AdamW(torch.optim.Optimizer):
                 s["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return s
 
+    @staticmethod
+    def _check(t, what):
+        if not t.is_cuda:
+            raise _lib.CseError(f"{what} is on {t.device}: the CUDA path has no CPU fallback")
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.is_sparse:
+            raise _lib.CseError(f"{what} must be a dense contiguous float32 tensor (got {t.dtype})")
+
     def _table(self, d, ps, amsgrad):
-        grads = [p.grad for p in ps]
-        key = tuple(t.data_ptr() for p in ps for t in (p, p.grad)) + (amsgrad,)
-        if d["key"] == key:
-            return
+        """Chunk table on the device.  Parameters and moments keep their storage from step to step; autograd hands
+        out new `.grad` storages (zero_grad(set_to_none=True), DDP bucket copies), so usually only the gradient
+        pointers change: they are rewritten in a rotating pinned staging copy and re-uploaded (one small H2D)."""
+        static_key = tuple(p.data_ptr() for p in ps) + (amsgrad,)
+        gptrs = [p.grad.data_ptr() for p in ps]
         n = len(ps)
-        numel = (C.c_longlong * n)(*[p.numel() for p in ps])
-        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
-        sts = [self._moments(p, amsgrad) for p in ps]
-        n_chunks = _lib.load().cse_optim_chunk_count(n, numel)
-        host = torch.empty(n_chunks * 48, dtype=torch.uint8).pin_memory()
-        _lib.call("cse_optim_table_fill", n, numel, arr(ps), arr(grads), arr([s["exp_avg"] for s in sts]),
-                  arr([s["exp_avg_sq"] for s in sts]),
-                  arr([s["max_exp_avg_sq"] for s in sts]) if amsgrad else None,
-                  C.c_void_p(host.data_ptr()), host.numel())
-        dev = ps[0].device
-        d.update(key=key, n_chunks=n_chunks, table=host.to(dev, non_blocking=True), keep=host,
-                 partial=torch.empty(n_chunks, dtype=torch.float32, device=dev))
+        if d["key"] != static_key:
+            for p in ps:
+                self._check(p, "parameter")
+            numel = (C.c_longlong * n)(*[p.numel() for p in ps])
+            arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+            sts = [self._moments(p, amsgrad) for p in ps]
+            n_chunks = _lib.load().cse_optim_chunk_count(n, numel)
+            hosts = [torch.empty(n_chunks * 48, dtype=torch.uint8).pin_memory() for _ in range(4)]
+            garr = (C.c_void_p * n)(*gptrs)
+            for h in hosts:
+                _lib.call("cse_optim_table_fill", n, numel, arr(ps), garr, arr([s["exp_avg"] for s in sts]),
+                          arr([s["exp_avg_sq"] for s in sts]),
+                          arr([s["max_exp_avg_sq"] for s in sts]) if amsgrad else None,
+                          C.c_void_p(h.data_ptr()), h.numel())
+            dev = ps[0].device
+            for t in (ps[0].grad, ps[-1].grad):
+                self._check(t, "gradient")
+            d.update(key=static_key, gptrs=None, numel=numel, n_chunks=n_chunks, hosts=hosts, turn=0,
+                     events=[None] * 4,
+                     table=torch.empty(n_chunks * 48, dtype=torch.uint8, device=dev),
+                     partial=torch.empty(n_chunks, dtype=torch.float32, device=dev))
+        if d["gptrs"] != gptrs:
+            slot = d["turn"] & 3
+            d["turn"] += 1
+            h = d["hosts"][slot]
+            if d["events"][slot] is not None:      # its previous upload (four refreshes ago) has been consumed
+                d["events"][slot].synchronize()
+            _lib.call("cse_optim_table_set_grads", n, d["numel"], (C.c_void_p * n)(*gptrs), C.c_void_p(h.data_ptr()),
+                      h.numel())
+            d["table"].copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            d["events"][slot] = ev
+            d["gptrs"] = gptrs
 
     # ---- the update --------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -91,12 +121,8 @@ class AdamW(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            for p in ps:
-                for t, what in ((p, "parameter"), (p.grad, "gradient")):
-                    if not t.is_cuda:
-                        raise _lib.CseError(f"{what} is on {t.device}: the CUDA path has no CPU fallback")
-                    if t.dtype != torch.float32 or not t.is_contiguous() or t.is_sparse:
-                        raise _lib.CseError(f"{what} must be a dense contiguous float32 tensor (got {t.dtype})")
+            if not ps[0].is_cuda:
+                raise _lib.CseError(f"parameter is on {ps[0].device}: the CUDA path has no CPU fallback")
             d = self._group_dev(gi, ps[0].device)
             self._table(d, ps, bool(group["amsgrad"]))
             _, gf, bf, gint = self._scaler

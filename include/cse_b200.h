@@ -479,6 +479,9 @@ CSE_API long long cse_optim_chunk_count(int n_tensors, const long long* numel);
 CSE_API int cse_optim_table_fill(int n_tensors, const long long* numel, void* const* param, void* const* grad,
                                  void* const* exp_avg, void* const* exp_avg_sq, void* const* max_exp_avg_sq,
                                  void* host_table, size_t host_table_bytes);
+/* Rewrites only the gradient pointers of a filled host table (autograd hands out new .grad storages every step). */
+CSE_API int cse_optim_table_set_grads(int n_tensors, const long long* numel, void* const* grad, void* host_table,
+                                      size_t host_table_bytes);
 CSE_API int cse_optim_step(const void* device_table, long long n_chunks, float lr, float beta1, float beta2,
                            float eps, float weight_decay, int amsgrad, float max_norm, int use_scaler,
                            float growth_factor, float backoff_factor, int growth_interval, int write_back_grads,
