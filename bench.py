@@ -111,6 +111,34 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def sample_once(self):
+        """One NVML query from the calling thread (the training leg: a polling thread beside its ~1000 launches per
+        step — in-process NVML as much as a looping nvidia-smi — slowed the step several-fold)."""
+        try:
+            import pynvml as n
+            if self.nvml is None:
+                n.nvmlInit()
+                visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+                self.handle = n.nvmlDeviceGetHandleByIndex(phys)
+                self.nvml = n
+                self._smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:  # noqa: BLE001
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            flags = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                     n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+            self.lines.append(",".join([str(sm), str(getattr(self, "_smax", "")), ""] +
+                                       ["Active" if mask & bit else "Not Active" for bit in flags]))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def summary(self):
+        """Summary of the samples taken with sample_once() (no polling thread to stop)."""
+        return self._summarise()
+
     def stop(self):
         if self.nvml is not None:
             self._stop.set()
@@ -123,6 +151,9 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        return self._summarise()
+
+    def _summarise(self):
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -433,6 +464,13 @@ def run_ours(args):
                            "unit": "TFLOP/s", "frac": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]},
         }
 
+    # The training leg runs BEFORE the legs that use the host cores (parity oracle, CPU baseline: 16 intra-op threads
+    # whose pool keeps spinning afterwards): its step is close to host launch-bound (~1000 launches per 18 ms) and
+    # measured 27 ms instead of 18 ms when it ran after them.
+    train = None
+    if not args.no_train:
+        train = measure_train(args, world, rank, local, dev, steps=max(3, min(args.steps, 10)), quiet=True)
+
     parity = None
     if rank == 0:
         est_bf16, pred_bf16 = step_device()
@@ -440,10 +478,6 @@ def run_ours(args):
         parity = parity_check(model, sd, mix_h, ctx_h, est_bf16, pred_bf16, dev)
     pipe.close()
     del pipe
-
-    train = None
-    if not args.no_train:
-        train = measure_train(args, world, rank, local, dev, steps=max(3, min(args.steps, 10)), quiet=True)
 
     cpu = None
     if rank == 0 and world == 1:
@@ -607,7 +641,7 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, k):
+    def timed(fn, k, sample_clocks=False):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -615,6 +649,12 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
         for _ in range(k):
             fn()
         e1.record()
+        if sample_clocks and rank == 0:
+            # the device is still executing the last enqueued step(s): clocks under load, while the query — slow when
+            # it has to wait for the driver lock (it cost ~2.5 ms per step when issued between steps) — delays only
+            # the host, after the closing event has been enqueued
+            sampler.sample_once()
+            sampler.sample_once()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
@@ -625,18 +665,17 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
             ms, wall = t[0].item(), t[1].item() / 1e3
         return ms, wall
 
-    sampler = ClockSampler(local)
-    if rank == 0 and not quiet:
-        sampler.start()
+    sampler = ClockSampler(local)   # sampled inline (sample_once) between timed steps, not by a polling thread
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
-    if rank == 0 and not quiet:
+    if rank == 0:
+        sampler.sample_once()       # NVML initialisation happens here, outside the timed region
         sampler.lines.clear()
     n0 = lib.cse_launch_count()
     loss0 = step_device()
     launches = lib.cse_launch_count() - n0
-    ms_total, _ = timed(step_device, steps)
+    ms_total, _ = timed(step_device, steps, sample_clocks=True)
     ms_step = ms_total / steps
     audio_s = TRAIN_BATCH * (Tt / SR) * world
     value = audio_s / (ms_step / 1e3)
@@ -659,7 +698,7 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
                 "allreduce_bytes_per_step": n_params * 4, "step_ms": ms_step, "step_ms_without_allreduce": ms_nosync / steps,
                 "exposed_allreduce_ms": exposed, "allreduce_alone_ms": alone,
                 "overlap_fraction": max(0.0, min(1.0, 1.0 - exposed / alone)) if alone > 0 else None}
-    clocks = sampler.stop() if (rank == 0 and not quiet) else None
+    clocks = sampler.summary() if rank == 0 else None
     if rank != 0:
         return None
     ps = shapes.path_shape(TRAIN_BATCH, Tt, CTX_TOKENS, SPK if loss_kind == "pit" else 1)

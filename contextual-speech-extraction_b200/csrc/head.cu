@@ -4,7 +4,10 @@
 // Reference: Dual_Path_Model_CSE.forward tail (ContSep.py:244-266), _over_add (ContSep.py:337-370),
 // Sepformer.forward mask/decode/length fix (ContSep.py:79-95; ContExt.py:116-129),
 // speechbrain Decoder = nn.ConvTranspose1d(256,1,16,stride=8,bias=False).
+#include <cstdlib>
+
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace cse {
 
@@ -141,6 +144,84 @@ __global__ void __launch_bounds__(256) decode_frames_kernel(const T* __restrict_
   }
 }
 
+// The same contraction on the tensor cores (bf16 mode): [rows, 256] x [256, 16] with mma.sync m16n8k16.  Under autocast
+// the reference's ConvTranspose1d runs in bf16 as well (its input mask * mix_w is cast), so v = relu(mask) * mix_w is
+// rounded to bf16 here too.  A warp takes 16 rows at a time: coalesced 16-byte loads of mask and mix_w, v staged as
+// bf16 in its own padded shared-memory tile, ldmatrix A fragments, the decoder filter as the B operand
+// (bf16, [16 taps][256 channels]) staged once per CTA and read by ldmatrix.  ~8 instructions per row instead of ~250: the SIMT
+// version's butterfly made it issue-bound at 0.12 of the HBM roofline.
+constexpr int kDfRowBytes = 2 * kN + 16;  // 528: consecutive rows land 4 banks apart -> conflict-free ldmatrix
+constexpr int kDfTile = 16 * kDfRowBytes;
+__global__ void __launch_bounds__(256) decode_frames_mma_kernel(const bf16* __restrict__ mask_pre,
+                                                                const bf16* __restrict__ E,
+                                                                const float* __restrict__ dec_w, int n_masks,
+                                                                size_t rows, float* __restrict__ frames) {
+  extern __shared__ __align__(16) unsigned char df_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  // the decoder filter as the B operand: [16 taps][256 channels] bf16 (K-major rows, padded like the A tiles),
+  // staged once per CTA; fragments come from ldmatrix each k-step
+  unsigned char* wtile = df_smem;
+  unsigned char* tile = df_smem + kDfTile + wid * kDfTile;
+  for (int idx = threadIdx.x; idx < kN * kEncK; idx += 256) {
+    const int c = idx / kEncK, tap = idx % kEncK;   // dec_w [256][16]: coalesced read
+    *reinterpret_cast<bf16*>(wtile + tap * kDfRowBytes + c * 2) = __float2bfloat16_rn(dec_w[idx]);
+  }
+  __syncthreads();
+  // ldmatrix x4 of B = (taps 0-7, k0) (taps 0-7, k0 + 8) (taps 8-15, k0) (taps 8-15, k0 + 8)
+  const uint32_t b_base = (uint32_t)__cvta_generic_to_shared(wtile) + ((lane & 7) + (lane >> 4) * 8) * kDfRowBytes +
+                          ((lane >> 3) & 1) * 16;
+  const size_t ntiles = (rows + 15) / 16;
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  for (size_t tl = (size_t)blockIdx.x * 8 + wid; tl < ntiles; tl += nwarps) {
+    const size_t r0 = tl * 16;
+    // stage v = relu(mask) * mix_w: lane -> 8 channels of a row, 16 rows
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const size_t r = r0 + i;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (r < rows) {
+        const f8 m = ld8(mask_pre + r * kN + lane * 8);
+        const f8 e = ld8(E + (r / n_masks) * kN + lane * 8);
+        u.x = pack_bf16(fmaxf(m.v[0], 0.f) * e.v[0], fmaxf(m.v[1], 0.f) * e.v[1]);
+        u.y = pack_bf16(fmaxf(m.v[2], 0.f) * e.v[2], fmaxf(m.v[3], 0.f) * e.v[3]);
+        u.z = pack_bf16(fmaxf(m.v[4], 0.f) * e.v[4], fmaxf(m.v[5], 0.f) * e.v[5]);
+        u.w = pack_bf16(fmaxf(m.v[6], 0.f) * e.v[6], fmaxf(m.v[7], 0.f) * e.v[7]);
+      }
+      *reinterpret_cast<uint4*>(tile + i * kDfRowBytes + lane * 16) = u;
+    }
+    __syncwarp();
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    // A fragments: ldmatrix x4 = (rows 0-7, k0) (rows 8-15, k0) (rows 0-7, k0 + 8) (rows 8-15, k0 + 8)
+    const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(tile) + ((lane & 7) + ((lane >> 3) & 1) * 8) * kDfRowBytes +
+                            (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      uint32_t a[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                   : "r"(a_base + ks * 32));
+      uint32_t w4[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                   : "r"(b_base + ks * 32));
+      mma_bf16_16816(c0, a, w4[0], w4[1]);
+      mma_bf16_16816(c1, a, w4[2], w4[3]);
+    }
+    __syncwarp();  // the tile is rewritten by the next iteration
+    // C fragments: (row g, taps 2 t4, 2 t4 + 1) and (row g + 8, ...), tap tile 0 / 1
+    const size_t ra = r0 + g, rb = ra + 8;
+    if (ra < rows) {
+      *reinterpret_cast<float2*>(frames + ra * kEncK + 2 * t4) = make_float2(c0[0], c0[1]);
+      *reinterpret_cast<float2*>(frames + ra * kEncK + 8 + 2 * t4) = make_float2(c1[0], c1[1]);
+    }
+    if (rb < rows) {
+      *reinterpret_cast<float2*>(frames + rb * kEncK + 2 * t4) = make_float2(c0[2], c0[3]);
+      *reinterpret_cast<float2*>(frames + rb * kEncK + 8 + 2 * t4) = make_float2(c1[2], c1[3]);
+    }
+  }
+}
+
 // est[b,t,s] = frames[(b,l,s), t-8l] + frames[(b,l-1,s), t-8(l-1)], l = t/8; zero beyond T_est
 // (F.pad branch, ContSep.py:92-93); only t < T is produced (trim branch, :95).
 __global__ void __launch_bounds__(256) decode_ola_kernel(const float* __restrict__ frames, int L,
@@ -185,7 +266,25 @@ int launch_mask_decode(const void* mask_pre, const void* E, const float* dec_w, 
                        int n_masks, int act, float* frames, float* est, cudaStream_t st) {
   const size_t rows = (size_t)B * L * n_masks;
   const int grid = (int)min((size_t)148 * 4, (rows + 7) / 8);
-  if (act == CSE_BF16)
+  static const bool simt_only = []() {  // CSE_DECODE_SIMT=1 keeps the SIMT kernel in bf16 mode (A/B aid)
+    const char* e = getenv("CSE_DECODE_SIMT");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (act == CSE_BF16 && E != nullptr && !simt_only) {
+    static DeviceOnce once;
+    if (!once.configured_on_this_device()) {
+      cudaError_t e = cudaFuncSetAttribute(decode_frames_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * kDfTile);
+      if (e != cudaSuccess) {
+        set_error("decode_frames: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return 1;
+      }
+      once.mark_configured();
+    }
+    const size_t tiles = (rows + 15) / 16;
+    const int gridm = (int)min((size_t)148 * 2, (tiles + 7) / 8);
+    decode_frames_mma_kernel<<<gridm, 256, 9 * kDfTile, st>>>((const bf16*)mask_pre, (const bf16*)E, dec_w, n_masks,
+                                                              rows, frames);
+  } else if (act == CSE_BF16)
     decode_frames_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)mask_pre, (const bf16*)E, dec_w,
                                                      n_masks, rows, frames);
   else

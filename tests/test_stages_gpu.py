@@ -228,11 +228,14 @@ def test_gate_and_mask_decode(prec):
     sd = {"decoder.weight": wd.double()}
     cols = [O.decoder(sd, (E.double() * mask[:, :, s]).transpose(1, 2)) for s in range(n_masks)]
     ref = O.fix_length(torch.stack(cols, -1), T)
-    assert rel_l2(est.cpu(), ref) < 5e-6
+    # bf16 mode: the decoder contraction runs on the tensor cores with mask * mix_w and the filter rounded to bf16,
+    # as the reference's ConvTranspose1d does under autocast (2^-9 per operand over 256 channels)
+    tol = 5e-6 if prec == FP32 else 4e-3
+    assert rel_l2(est.cpu(), ref) < tol
     assert torch.all(est[:, 8 * (L - 1) + 16:].cpu() == 0)
     # trim branch
     T2 = 8 * (L - 1) + 16 - 3
     est2 = torch.empty(B, T2, n_masks, device=DEV)
     _lib.call("cse_mask_decode", _p(mp.to(DEV)), _p(E.to(DEV)), _p(wd.to(DEV)), B, L, T2, n_masks, prec,
               _p(frames), _p(est2), _st())
-    assert rel_l2(est2.cpu(), ref[:, :T2]) < 5e-6
+    assert rel_l2(est2.cpu(), ref[:, :T2]) < tol
