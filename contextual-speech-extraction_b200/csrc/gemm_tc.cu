@@ -17,9 +17,9 @@
 //                 TMA store.  The fp32 residual update
 //                 R += A W^T + b is a TMA REDUCE-ADD (cp.reduce.async.bulk.tensor .add), so the
 //                 residual stream is never loaded into the SM; the M tail is clipped by TMA.
-// Opt-in variants, measured slower and kept for A/B runs (profiles/r01_experiments.md, tests/test_variants_gpu.py):
-// PAIR = cta_group::2 UMMA over the CTA pair (CSE_GEMM_PAIR=1), ARES = A tile resident across n-tiles
-// (CSE_GEMM_ARES=1).  CSE_DBG_* macros strip parts of the kernel for tools/gemm_variants.py.
+// (Two round-1 variants — one cta_group::2 UMMA per CTA pair, and an A tile resident across n-tiles — measured slower,
+// profiles/r01_experiments.md, and were removed in round 2.)  CSE_DBG_* macros strip parts of the kernel for
+// tools/gemm_variants.py.
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.  The kernel is launched
 // with programmatic dependent launch: its prologue overlaps the previous kernel's tail (pdl_wait()).
 #include <cuda.h>
@@ -44,12 +44,6 @@ constexpr int kUmmaK = 16;
 #endif
 #ifndef CSE_EPI_ROW_BYTES
 #define CSE_EPI_ROW_BYTES 128  // bytes per row of one epilogue staging chunk: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
-#endif
-#ifndef CSE_PAIR_STAGES
-#define CSE_PAIR_STAGES 5
-#endif
-#ifndef CSE_PAIR_EPIBUFS
-#define CSE_PAIR_EPIBUFS 2
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -94,22 +88,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return tc
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-// PAIR = one 256 x BN UMMA (cta_group::2) per CTA pair: each CTA stages its own 128 A rows and only
-// HALF of the weight tile, so a stage is 32 KB instead of 48 KB and the shared memory this frees
-// goes to a deeper load ring and a second epilogue staging chunk per warp.
-// ARES (K == 256 with several n-tiles: QKV, FFN1) = the 128 x 256 A tile stays RESIDENT in shared memory
-// (4 k-blocks, 64 KB) while the CTA walks the n-tiles of its rows, so A crosses the L2 once per row tile
-// instead of once per (row tile, n-tile); the ring stages then hold weight tiles only.  These GEMMs are
-// bound by L2 throughput (~10 TB/s for operand loads + output stores together), not by HBM or the MMAs.
-template <int BN, bool PAIR, bool ARES = false, bool LNE = false>
+template <int BN, bool LNE = false>
 struct TcCfg {
   // LNE (K = 256: four k-blocks per tile, an epilogue-bound kernel): three ring stages are enough, and the 48 KB
   // they free hold the bias / gamma / beta vectors (read from global memory per piece they cost an L2 round trip
   // each: the L1 left beside 225 KB of shared memory does not keep them)
-  static constexpr int kStages = LNE ? 3 : (PAIR ? CSE_PAIR_STAGES : ((BN == 256) ? CSE_STAGES_256 : 6));
+  static constexpr int kStages = LNE ? 3 : ((BN == 256) ? CSE_STAGES_256 : 6);
   static constexpr int kABytes = kTM * kTK * 2;  // 16 KB
-  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kTK * 2;
-  static constexpr int kAStages = ARES ? 4 : kStages;  // ARES: one slot per k-block of the resident tile
+  static constexpr int kBBytes = BN * kTK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;   // bytes one k-block brings in (A + W)
   static constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
   static constexpr int kEpiWarps = (BN == 256) ? CSE_EPI_WARPS : 8;  // 4 TMEM lane quarters x column groups
@@ -118,10 +104,10 @@ struct TcCfg {
   // has TWO chunks, so the TMA store of one chunk drains while the next is being converted (a 4 KB
   // store takes ~0.8 us to release its source when the write path is busy, as long as the conversion).
   static constexpr int kRowBytes = CSE_EPI_ROW_BYTES;
-  static constexpr int kEpiBufs = (PAIR ? CSE_PAIR_EPIBUFS : 1) * (128 / kRowBytes);
+  static constexpr int kEpiBufs = 128 / kRowBytes;
   static constexpr int kEpiBufBytes = 32 * kRowBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
-  static constexpr int kRingBytes = kAStages * kABytes + kStages * kBBytes;
+  static constexpr int kRingBytes = kStages * (kABytes + kBBytes);
   static constexpr int kVecBytes = LNE ? 3 * 256 * 4 : 0;   // bias, gamma, beta
   static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kRingBytes + kEpiBytes + 384 + kVecBytes;
 };
@@ -145,22 +131,21 @@ struct LnEpilogue {
 // the canonical MN-major atom stack, 8 token-rows per atom), two per 128 output rows / four per 256 output columns;
 // descriptors: SBO = 1024 B between 8-token groups, LBO = 8192 B between 64-feature blocks; a K = 16 step advances
 // two atoms (2048 B).  No transposed copies of the operands exist (they were 6 ms of a 28.6 ms training step).
-template <int BN, bool OUT_F32, bool PAIR, bool ARES, bool LNE = false, int MNM = 0>
-__global__ void __launch_bounds__((TcCfg<BN, PAIR, ARES, LNE>::kThreads), 1)
+template <int BN, bool OUT_F32, bool LNE = false, int MNM = 0>
+__global__ void __launch_bounds__((TcCfg<BN, LNE>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                float bias_scale, int accumulate_into_c, void* Cout, int ldc, int M, int N, int K,
                int relu, int ksplit, LnEpilogue ln) {
-  using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
-  static_assert(!LNE || (BN == 256 && OUT_F32 && !PAIR && !ARES && Cfg::kEpiWarps == 8),
+  using Cfg = TcCfg<BN, LNE>;
+  static_assert(!LNE || (BN == 256 && OUT_F32 && Cfg::kEpiWarps == 8),
                 "the LayerNorm epilogue is built on the 256-wide fp32 per-CTA variant");
-  static_assert(MNM == 0 || (!PAIR && !ARES && !LNE), "MN-major operands: per-CTA variant only");
+  static_assert(MNM == 0 || !LNE, "MN-major operands and the LayerNorm epilogue are separate variants");
   pdl_launch_dependents();
-  static_assert(!(ARES && PAIR), "resident-A mode is built on the per-CTA UMMA variant");
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + Cfg::kAStages * Cfg::kABytes;
+  const uint32_t sB = smem_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t sEpi = smem_base + Cfg::kRingBytes;  // multiple of 1024
   const uint32_t sBar = sEpi + Cfg::kEpiBytes;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
@@ -168,9 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_empty = sBar + 8 * Cfg::kStages;
   const uint32_t bar_tfull = sBar + 16 * Cfg::kStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  const uint32_t bar_afull = bar_tempty + 16;   // ARES: [4] resident-A k-block landed
-  const uint32_t bar_aempty = bar_afull + 32;   // ARES: [4] resident-A k-block no longer read by any MMA
-  const uint32_t tmem_slot = bar_aempty + 32;
+  const uint32_t tmem_slot = bar_tempty + 16;
   const uint32_t sVec = sBar + 384;  // LNE: bias[256], gamma[256], beta[256]
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
@@ -189,32 +172,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int cta_rank = (int)cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int total_pt = ((m_tiles + 1) >> 1) * n_tiles * ksplit;
-  // Tile walk.  Default: pair p takes tiles p, p + npairs, ... (n fastest, so the pairs that share an
-  // A tile run at the same time).  ARES: pair p takes a CONTIGUOUS run of tiles, so consecutive tiles
-  // share their row tile and A is (re)loaded only when the row tile changes.
-  const int t_begin = ARES ? (int)((long long)pair_id * total_pt / npairs) : pair_id;
-  const int t_end = ARES ? (int)((long long)(pair_id + 1) * total_pt / npairs) : total_pt;
-  const int t_step = ARES ? 1 : npairs;
+  // Tile walk: pair p takes tiles p, p + npairs, ... (n fastest, so the pairs that share an A tile run at the same time)
+  const int t_begin = pair_id, t_end = total_pt, t_step = npairs;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, PAIR ? 1 : 2);  // !PAIR: released by the MMA issuers of BOTH CTAs
-    }
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(bar_afull + 8 * s, 1);
-      mbar_init(bar_aempty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 2);  // released by the MMA issuers of BOTH CTAs
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      // one arrive per epilogue warp; PAIR: the leader's barrier collects both CTAs' warps
-      mbar_init(bar_tempty + 8 * s, PAIR ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);
+      mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);  // same warp id in both CTAs
-    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
   if constexpr (LNE) {  // parameters, not produced by the previous kernel: may be read before pdl_wait()
     float* vec = reinterpret_cast<float*>(smem_aligned + (sVec - smem_base));
@@ -234,11 +207,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA producer =================
     // The whole warp walks the loop (keeps it convergent for the teardown barrier); lane 0 acts.
-    uint32_t stage = 0, phase = 0, seg = 0;
+    uint32_t stage = 0, phase = 0;
     for (int pt = t_begin; pt < t_end; pt += t_step) {
       const int tl = pt / ksplit, ks = pt - tl * ksplit;
       const int m0 = (2 * (tl / n_tiles) + cta_rank) * kTM, n0 = (tl % n_tiles) * BN;
-      const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
       const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
       if constexpr (LNE) {
         // the residual rows this tile's epilogue will read, one tile of lead: HBM -> L2 now, so that the epilogue's
@@ -249,28 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(rbase + (size_t)i * 128));
       }
       for (int kb = kb0; kb < kb1; ++kb) {
-        if constexpr (ARES) {
-          if (lane == 0) {
-            if (new_rows) {  // k-block kb of the previous row tile has been consumed by its last MMA
-              mbar_wait_spin(bar_aempty + 8 * kb, (seg & 1u) ^ 1u, 5);
-              mbar_expect_tx(bar_afull + 8 * kb, Cfg::kABytes);
-              tma_load_2d(sA + kb * Cfg::kABytes, &tmA, bar_afull + 8 * kb, kb * kTK, m0);
-            }
-            mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
-            mbar_expect_tx(bar_full + 8 * stage, Cfg::kBBytes);
-            tma_load_2d_mcast(sB + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / 2), &tmB,
-                              bar_full + 8 * stage, kb * kTK, n0 + cta_rank * (BN / 2), (uint16_t)3);
-          }
-        } else if constexpr (PAIR) {
-          if (lane == 0) {
-            mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);  // the pair's UMMAs have consumed this stage
-            // all four boxes of the pair (2 x A rows, 2 x W halves) complete on the LEADER's barrier
-            const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
-            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(sA + stage * Cfg::kABytes, &tmA, lead_full, kb * kTK, m0);
-            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, lead_full, kb * kTK, n0 + cta_rank * (BN / 2));
-          }
-        } else if constexpr (MNM != 0) {
+        if constexpr (MNM != 0) {
           if (lane == 0) {
             mbar_wait_spin(bar_empty + 8 * stage, phase ^ 1, 1);   // both CTAs have consumed this stage
             mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
@@ -300,19 +251,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (new_rows) ++seg;
     }
   } else if (warp == 1) {
     // ================= MMA issuer (lane 0 issues; warp stays convergent) =================
-    // PAIR: only the leader CTA issues; each UMMA is 256 x BN x 16 across both SMs (A rows and the
-    // weight halves come from the same shared-memory offsets in both CTAs, D lands in both TMEMs).
-    constexpr uint32_t idesc = MNM != 0 ? tc::make_idesc_bf16(kTM, BN, MNM == 1 ? 1 : 0, 1)
-                                        : make_idesc_bf16(PAIR ? 2 * kTM : kTM, BN);
-    uint32_t stage = 0, phase = 0, astage = 0, aphase = 0, seg = 0;
-    for (int pt = t_begin; pt < t_end && (!PAIR || cta_rank == 0); pt += t_step) {
-      const bool new_rows = ARES && (pt == t_begin || pt % n_tiles == 0);
-      const bool last_use = ARES && (pt + 1 == t_end || (pt + 1) % n_tiles == 0);
-      if (new_rows && pt != t_begin) ++seg;
+    constexpr uint32_t idesc = MNM != 0 ? tc::make_idesc_bf16(kTM, BN, MNM == 1 ? 1 : 0, 1) : make_idesc_bf16(kTM, BN);
+    uint32_t stage = 0, phase = 0, astage = 0, aphase = 0;
+    for (int pt = t_begin; pt < t_end; pt += t_step) {
       if (lane == 0) {
         mbar_wait_spin(bar_tempty + 8 * astage, aphase ^ 1, 2);
         tc_fence_after();
@@ -323,11 +267,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
         if (lane == 0) {
-          if (new_rows) mbar_wait_spin(bar_afull + 8 * kb, seg & 1u, 6);
           mbar_wait_spin(bar_full + 8 * stage, phase, 3);
           tc_fence_after();
           const uint64_t adesc = MNM == 1 ? make_mnmajor_sw128_desc(sA + stage * Cfg::kABytes)
-                                          : make_kmajor_sw128_desc(sA + (ARES ? kb : (int)stage) * Cfg::kABytes);
+                                          : make_kmajor_sw128_desc(sA + stage * Cfg::kABytes);
           const uint64_t bdesc = MNM != 0 ? make_mnmajor_sw128_desc(sB + stage * Cfg::kBBytes)
                                           : make_kmajor_sw128_desc(sB + stage * Cfg::kBBytes);
           if constexpr (MNM != 0) {
@@ -341,22 +284,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kTK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
 #ifndef CSE_DBG_NOMMA
-            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
 #endif
           }
           // release the stage in both CTAs
-          if constexpr (PAIR) umma_commit_pair_mcast(bar_empty + 8 * stage, (uint16_t)3);
-          else umma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
-          if (last_use) umma_commit(bar_aempty + 8 * kb);  // resident A k-block free for the next row tile
+          umma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) {  // accumulator complete -> epilogue (PAIR: of both CTAs)
-        if constexpr (PAIR) umma_commit_pair_mcast(bar_tfull + 8 * astage, (uint16_t)3);
-        else umma_commit(bar_tfull + 8 * astage);
-      }
+      if (lane == 0) umma_commit(bar_tfull + 8 * astage);  // accumulator complete -> epilogue
       __syncwarp();
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
@@ -585,8 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * astage, 0));
-        else mbar_arrive(bar_tempty + 8 * astage);
+        mbar_arrive(bar_tempty + 8 * astage);
       }
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
@@ -599,8 +535,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   cluster_sync_all();  // neither CTA retires while the peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
-    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -699,14 +634,14 @@ int sm_count() {  // of the CURRENT device (cached per ordinal)
   return n;
 }
 
-template <int BN, bool OUT_F32, bool PAIR, bool ARES = false, bool LNE = false, int MNM = 0>
+template <int BN, bool OUT_F32, bool LNE = false, int MNM = 0>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const float* bias, float bias_scale, int accumulate, void* C, int ldc, int M,
                           int N, int K, int relu, cudaStream_t st, int ksplit = 1, LnEpilogue ln = LnEpilogue{}) {
-  using Cfg = TcCfg<BN, PAIR, ARES, LNE>;
+  using Cfg = TcCfg<BN, LNE>;
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE, MNM>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_F32, LNE, MNM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", Cfg::kSmem, cudaGetErrorString(e));
@@ -718,7 +653,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, PAIR, ARES, LNE, MNM>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
+  cudaError_t le = launch_pdl(gemm_tc_kernel<BN, OUT_F32, LNE, MNM>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, 2, tmA, tmB, tmC, bias, bias_scale,
                                       accumulate, C, ldc, M, N, K, relu, ksplit, ln);
   if (le != cudaSuccess) {
     set_error("gemm_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
@@ -752,28 +687,12 @@ int launch_gemm_tc(const bf16* A, int lda, const bf16* W, const float* bias, flo
                      out_fp32 ? 4 : 2, &tmC))
     return 1;
   const int acc = residual != nullptr ? 1 : 0;
-  static const bool pair_mma = []() {  // CSE_GEMM_PAIR=1 selects the cta_group::2 pair-UMMA variant (measured slower: A/B aid)
-    const char* e = getenv("CSE_GEMM_PAIR");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (BN == 256 && pair_mma) {
-    return out_fp32 ? launch_tc_impl<256, true, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
-  }
-  static const bool a_resident = []() {  // CSE_GEMM_ARES=1 selects the resident-A variant (measured slower: A/B aid)
-    const char* e = getenv("CSE_GEMM_ARES");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (BN == 256 && K == 4 * kTK && N > BN && a_resident) {
-    return out_fp32 ? launch_tc_impl<256, true, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false, false, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
-  }
   if (BN == 256) {
-    return out_fp32 ? launch_tc_impl<256, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                    : launch_tc_impl<256, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+    return out_fp32 ? launch_tc_impl<256, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                    : launch_tc_impl<256, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
   }
-  return out_fp32 ? launch_tc_impl<128, true, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
-                  : launch_tc_impl<128, false, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
+  return out_fp32 ? launch_tc_impl<128, true>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st)
+                  : launch_tc_impl<128, false>(tmA, tmB, tmC, bias, bias_scale, acc, C, ldc, M, N, K, relu, st);
 }
 
 // R[M,256] += A[M,K] W[256,K]^T + b in place, H[M,256] = LayerNorm(R) (bf16): out-proj + residual + norm2 of a
@@ -797,7 +716,7 @@ int launch_gemm_tc_residual_ln(const bf16* A, int lda, const bf16* W, const floa
   if (get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kTM, kTK, 2, &tmA)) return 1;
   if (get_tensor_map(W, (uint64_t)kN, (uint64_t)K, (uint64_t)K, 128, kTK, 2, &tmB)) return 1;  // half tile per CTA
   LnEpilogue ln{R, gamma, beta, H, eps};
-  return launch_tc_impl<256, true, false, false, true>(tmA, tmB, tmA /*unused*/, bias, 1.f, 0, R, kN, M, kN, K, 0, st, 1, ln);
+  return launch_tc_impl<256, true, true>(tmA, tmB, tmA /*unused*/, bias, 1.f, 0, R, kN, M, kN, K, 0, st, 1, ln);
 }
 
 // C[M,N] = A[M,K] W[K,N] for the row-major bf16 W [K, N] as nn.Linear stores it ([out, in]): the input gradient
@@ -821,10 +740,10 @@ int launch_gemm_tc_dgrad(const bf16* A, int lda, const bf16* W, int ldw, void* C
                      out_fp32 ? 4 : 2, &tmC))
     return 1;
   if (BN == 256)
-    return out_fp32 ? launch_tc_impl<256, true, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
-                    : launch_tc_impl<256, false, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
-  return out_fp32 ? launch_tc_impl<128, true, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
-                  : launch_tc_impl<128, false, false, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
+    return out_fp32 ? launch_tc_impl<256, true, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
+                    : launch_tc_impl<256, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
+  return out_fp32 ? launch_tc_impl<128, true, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st)
+                  : launch_tc_impl<128, false, false, 2>(tmA, tmB, tmC, nullptr, 0.f, 0, C, ldc, M, N, K, 0, st);
 }
 
 // C[M,N] (fp32) += X^T Y for row-major bf16 X [T, M] (ldx), Y [T, N] (ldy), contracted over the T tokens and split
@@ -854,8 +773,8 @@ int launch_gemm_tc_wgrad(const bf16* X, int ldx, const bf16* Y, int ldy, float* 
   const int kb_per = ceil_div(num_kb, want);
   const int ksplit = ceil_div(num_kb, kb_per);
   return BN == 256
-             ? launch_tc_impl<256, true, false, false, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit)
-             : launch_tc_impl<128, true, false, false, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit);
+             ? launch_tc_impl<256, true, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit)
+             : launch_tc_impl<128, true, false, 1>(tmX, tmY, tmC, nullptr, 0.f, 1, C, ldc, M, N, Tk, 0, st, ksplit);
 }
 
 // C[M,N] (fp32) += A[M,K] W[N,K]^T with the K dimension split over CTAs: the weight-gradient shape (M, N = a layer's
@@ -883,8 +802,8 @@ int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float*
   if (want < 1) want = 1;
   const int kb_per = ceil_div(num_kb, want);
   const int ksplit = ceil_div(num_kb, kb_per);      // no empty job
-  return BN == 256 ? launch_tc_impl<256, true, false>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit)
-                   : launch_tc_impl<128, true, false>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit);
+  return BN == 256 ? launch_tc_impl<256, true>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit)
+                   : launch_tc_impl<128, true>(tmA, tmB, tmC, nullptr, 0.f, 1, C, ldc, M, N, K, 0, st, ksplit);
 }
 
 }  // namespace cse

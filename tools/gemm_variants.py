@@ -17,7 +17,7 @@ NVCC = "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden"]
 
-BASE = ["-DCSE_EPI_WARPS=8", "-DCSE_STAGES_256=4", "-DCSE_PAIR_STAGES=5", "-DCSE_PAIR_EPIBUFS=2"]
+BASE = ["-DCSE_EPI_WARPS=8", "-DCSE_STAGES_256=4"]
 VARIANTS = {
     "r128": BASE + ["-DCSE_EPI_ROW_BYTES=128"],
     "r64": BASE + ["-DCSE_EPI_ROW_BYTES=64"],
@@ -74,7 +74,7 @@ def run(names):
         lib.cse_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.cse_last_error.restype = C.c_char_p
-        line = [f"{name:12s} pair={os.environ.get('CSE_GEMM_PAIR', '0')} ares={os.environ.get('CSE_GEMM_ARES', '0')}"]
+        line = [f"{name:12s}"]
         for tag, N, K, relu, resid in (shapes if not name.startswith("ffn_") else []):
             A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
             W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
