@@ -52,7 +52,14 @@ int launch_prelu_ola(const float* X, const float* prelu, int B, int S, int L, in
   return check_launch("prelu_ola_kernel");
 }
 
-// out = tanh(o) * sigmoid(g), 8 elements per thread.
+// out = tanh(o) * sigmoid(g), 8 elements per thread.  bf16 mode: one MUFU.TANH per function (sigmoid(x) =
+// 0.5 + 0.5 tanh(x / 2); tanh.approx is good to 2^-11, the bf16 result to 2^-9) — libm tanhf + expf + a division
+// made the kernel XU-bound (59 % XU, 0.44 of the HBM roofline).  fp32 mode keeps the libm functions.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) gate_kernel(const T* o, const T* g,
                                                    size_t n8, T* out) {  // out may alias o
@@ -60,7 +67,10 @@ __global__ void __launch_bounds__(256) gate_kernel(const T* o, const T* g,
     const f8 a = ld8(o + i * 8), b = ld8(g + i * 8);
     f8 r;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = tanhf(a.v[k]) * (1.0f / (1.0f + expf(-b.v[k])));
+    for (int k = 0; k < 8; ++k) {
+      if constexpr (sizeof(T) == 2) r.v[k] = tanh_approx(a.v[k]) * fmaf(0.5f, tanh_approx(0.5f * b.v[k]), 0.5f);
+      else r.v[k] = tanhf(a.v[k]) * (1.0f / (1.0f + expf(-b.v[k])));
+    }
     st8(out + i * 8, r);
   }
 }
@@ -150,6 +160,11 @@ __global__ void __launch_bounds__(256) decode_frames_kernel(const T* __restrict_
 // bf16 in its own padded shared-memory tile, ldmatrix A fragments, the decoder filter as the B operand
 // (bf16, [16 taps][256 channels]) staged once per CTA and read by ldmatrix.  ~8 instructions per row instead of ~250: the SIMT
 // version's butterfly made it issue-bound at 0.12 of the HBM roofline.
+__device__ __forceinline__ uint4 ldg128_ordered(const void* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
 constexpr int kDfRowBytes = 2 * kN + 16;  // 528: consecutive rows land 4 banks apart -> conflict-free ldmatrix
 constexpr int kDfTile = 16 * kDfRowBytes;
 __global__ void __launch_bounds__(256) decode_frames_mma_kernel(const bf16* __restrict__ mask_pre,
@@ -175,20 +190,38 @@ __global__ void __launch_bounds__(256) decode_frames_mma_kernel(const bf16* __re
   const size_t nwarps = (size_t)gridDim.x * 8;
   for (size_t tl = (size_t)blockIdx.x * 8 + wid; tl < ntiles; tl += nwarps) {
     const size_t r0 = tl * 16;
-    // stage v = relu(mask) * mix_w: lane -> 8 channels of a row, 16 rows
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const size_t r = r0 + i;
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (r < rows) {
-        const f8 m = ld8(mask_pre + r * kN + lane * 8);
-        const f8 e = ld8(E + (r / n_masks) * kN + lane * 8);
-        u.x = pack_bf16(fmaxf(m.v[0], 0.f) * e.v[0], fmaxf(m.v[1], 0.f) * e.v[1]);
-        u.y = pack_bf16(fmaxf(m.v[2], 0.f) * e.v[2], fmaxf(m.v[3], 0.f) * e.v[3]);
-        u.z = pack_bf16(fmaxf(m.v[4], 0.f) * e.v[4], fmaxf(m.v[5], 0.f) * e.v[5]);
-        u.w = pack_bf16(fmaxf(m.v[6], 0.f) * e.v[6], fmaxf(m.v[7], 0.f) * e.v[7]);
+    // stage v = relu(mask) * mix_w: lane -> 8 channels of a row, 16 rows.  The 16 loads of an 8-row batch are
+    // issued before any of them is used (row index clamped, not branched on: a predicated load is not hoisted over
+    // its guard, and the row-at-a-time version spent one DRAM round trip per row — 0.22 of the HBM roofline)
+    // (volatile asm loads keep their program order, so the compiler cannot sink them next to their uses; the
+    // mix_w row of row r0 + i is q0 + (rem0 + i) / n_masks: one division per tile, a multiply-shift per row)
+    const uint32_t last = (uint32_t)min((size_t)15, rows - 1 - r0), nm = (uint32_t)n_masks;
+    const uint32_t q0 = (uint32_t)r0 / nm, rem0 = (uint32_t)r0 - q0 * nm, inv = (256u + nm - 1u) / nm;
+    const bf16* mrow = mask_pre + r0 * kN + lane * 8;
+    const bf16* erow = E + (size_t)q0 * kN + lane * 8;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      uint4 mq[8], eq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ri = min((uint32_t)(hb * 8 + i), last);
+        mq[i] = ldg128_ordered(mrow + (size_t)ri * kN);
+        eq[i] = ldg128_ordered(erow + (size_t)(((rem0 + ri) * inv) >> 8) * kN);
       }
-      *reinterpret_cast<uint4*>(tile + i * kDfRowBytes + lane * 16) = u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq[i]);
+        const __nv_bfloat162* eh = reinterpret_cast<const __nv_bfloat162*>(&eq[i]);
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 m = __bfloat1622float2(mh[j]), e = __bfloat1622float2(eh[j]);
+          w[j] = pack_bf16(fmaxf(m.x, 0.f) * e.x, fmaxf(m.y, 0.f) * e.y);
+        }
+        const bool live = r0 + hb * 8 + i < rows;   // rows past the end stage zeros
+        *reinterpret_cast<uint4*>(tile + (hb * 8 + i) * kDfRowBytes + lane * 16) =
+            live ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     __syncwarp();
     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
