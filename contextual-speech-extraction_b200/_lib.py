@@ -80,6 +80,7 @@ _SIGNATURES = {
                              C.c_int, C.c_int, C.c_int, _v]),
     "cse_layernorm_fwd": (C.c_int, [_v, _v, _v, C.c_int, C.c_float, C.c_int, _v, _v]),
     "cse_ln_linear": (C.c_int, [_v, _v, _v, C.c_float, _v, _v, _v, C.c_int, C.c_int, C.c_int, C.c_int, _v]),
+    "cse_ffn_ln_fused": (C.c_int, [_v, _v, _v, C.c_float, _v, _v, _v, _v, _v, _v, _v, _v, C.c_int, _v]),
     "cse_linear_residual_ln": (C.c_int, [_v, C.c_int, _v, _v, _v, _v, _v, C.c_float, _v, C.c_int, C.c_int, _v]),
     "cse_ffn_fused": (C.c_int, [_v, _v, _v, _v, _v, _v, C.c_int, _v]),
     "cse_attention_fwd": (C.c_int, [_v, C.c_int, C.c_int, C.c_int, _v, _v]),

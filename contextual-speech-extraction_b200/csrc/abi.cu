@@ -204,6 +204,17 @@ static bool outproj_ln_fused_enabled() {
   return on;
 }
 
+// The two LayerNorms of a layer ride along in the feed-forward kernel (ffn_tc.cu, LNF variant): norm2 in its own
+// LayerNorm warps ahead of the tensor pipe, norm1 of the NEXT layer in its output warps — four launches per layer.
+// CSE_FFN_LN=0 keeps the separate layernorm_kernel launches (A/B aid).
+static bool ffn_ln_fused_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSE_FFN_LN");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 // CSE_LN_FUSED=1 runs norm1 -> in_proj as one kernel (gemm_ln_tc.cu).  Off by default: measured 123-132 us
 // against 36 + 67 us for the two kernels (its LayerNorm warps cannot keep enough loads in flight inside the
 // 96 registers a 576-thread CTA leaves them), profiles/r01_experiments.md.
@@ -226,9 +237,15 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
   void* AO = ws + pl.AO;
   void* F1 = ws + pl.F1;
   const int act = pl.precision;
+  const bool ffn_ln = pl.precision == CSE_BF16 && ffn_fused_enabled() && ffn_ln_fused_enabled() &&
+                      !ln_qkv_fused_enabled() && !outproj_ln_fused_enabled();
   for (int l = 0; l < CSE_LAYERS; ++l) {
     const cse_layer_params& lp = sp.layer[l];
-    if (pl.precision == CSE_BF16 && ln_qkv_fused_enabled()) {
+    if (ffn_ln && l > 0) {
+      // norm1(R) is already in H: the previous layer's feed-forward kernel wrote it
+      if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
+                 3 * kN, kN, 0, 0, st)) return 1;
+    } else if (pl.precision == CSE_BF16 && ln_qkv_fused_enabled()) {
       // norm1 -> in_proj in one kernel: the residual row is read once and normalised in the GEMM's A producer
       CSE_REQUIRE(lp.in_proj_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
       if (launch_gemm_ln_tc(R, lp.ln1_g, lp.ln1_b, 1e-6f, (const bf16*)lp.in_proj_w_bf16, lp.in_proj_b,
@@ -247,7 +264,17 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
     } else {
       if (linear(pl, AO, kN, lp.out_proj_w, lp.out_proj_w_bf16, lp.out_proj_b, 1.f, R, R, kN, M, kN, kN,
                  0, 1, st)) return 1;
-      if (launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+      if (!ffn_ln && launch_layernorm(R, lp.ln2_g, lp.ln2_b, M, 1e-6f, act, H, st)) return 1;
+    }
+    if (ffn_ln) {
+      // norm2 -> Linear -> ReLU -> Linear -> +R -> next layer's norm1, one kernel; AO (consumed by out_proj) is the
+      // scratch that receives norm2(R)
+      CSE_REQUIRE(lp.ffn1_w_bf16 && lp.ffn2_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
+      const cse_layer_params* nx = l + 1 < CSE_LAYERS ? &sp.layer[l + 1] : nullptr;
+      if (launch_ffn_tc_ln(R, lp.ln2_g, lp.ln2_b, 1e-6f, (bf16*)AO, (const bf16*)lp.ffn1_w_bf16, lp.ffn1_b,
+                           (const bf16*)lp.ffn2_w_bf16, lp.ffn2_b, nx ? nx->ln1_g : nullptr,
+                           nx ? nx->ln1_b : nullptr, nx ? (bf16*)H : nullptr, M, st)) return 1;
+      continue;
     }
     if (pl.precision == CSE_BF16 && ffn_fused_enabled()) {
       // Linear -> ReLU -> Linear -> residual add in one kernel: the [M,1024] hidden never leaves the SM
@@ -716,6 +743,14 @@ int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, cons
   CSE_REQUIRE(A_bf16 && W1_bf16 && b1 && W2_bf16 && b2 && R, "ffn_fused: NULL argument");
   return launch_ffn_tc((const bf16*)A_bf16, (const bf16*)W1_bf16, b1, (const bf16*)W2_bf16, b2, R, M,
                        (cudaStream_t)stream);
+}
+
+int cse_ffn_ln_fused(float* R, const float* ln2_g, const float* ln2_b, float eps, void* scratch_bf16,
+                     const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                     const float* next_ln1_g, const float* next_ln1_b, void* H1_bf16, int M, void* stream) {
+  CSE_REQUIRE(R && ln2_g && ln2_b && scratch_bf16 && W1_bf16 && b1 && W2_bf16 && b2, "ffn_ln_fused: NULL argument");
+  return launch_ffn_tc_ln(R, ln2_g, ln2_b, eps, (bf16*)scratch_bf16, (const bf16*)W1_bf16, b1, (const bf16*)W2_bf16,
+                          b2, next_ln1_g, next_ln1_b, (bf16*)H1_bf16, M, (cudaStream_t)stream);
 }
 
 int cse_layernorm_fwd(const float* x, const float* g, const float* b, int M, float eps, int act_dtype,

@@ -249,7 +249,7 @@ __device__ __forceinline__ void attn_tile(const bf16* Qs, const bf16* Ks, const 
 
 // HPC = heads per CTA (1: eight warps share one head's query tiles; 8: one warp per head).
 template <int HPC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, HPC == 8 ? 3 : 2)
 attention_bf16_kernel(const bf16* __restrict__ qkv, int n, int n_pad, bf16* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kThreads = 256;

@@ -98,21 +98,49 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Row LayerNorm of 256 channels held as 8 per lane; two-pass (mean, then centred variance).
-__device__ __forceinline__ void ln_row(f8& x, const f8& g, const f8& b, float eps) {
-  float s = 0.f;
+// Row LayerNorm of 256 channels held as 8 per lane; two-pass (mean, then centred variance).  NR rows at once: the
+// per-row arithmetic is the same for every NR (same results), but the NR butterfly reductions advance together —
+// NR independent shuffles per step instead of NR dependent chains of five.
+template <int NR>
+__device__ __forceinline__ void ln_rows(f8 (&x)[NR], const f8& g, const f8& b, float eps) {
+  float s[NR];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += x.v[i];
-  const float mean = warp_sum(s) * (1.0f / kN);
-  float q = 0.f;
+  for (int r = 0; r < NR; ++r) {
+    s[r] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    x.v[i] -= mean;
-    q += x.v[i] * x.v[i];
+    for (int i = 0; i < 8; ++i) s[r] += x[r].v[i];
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kN) + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x.v[i] = x.v[i] * rstd * g.v[i] + b.v[i];
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  float q[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float mean = s[r] * (1.0f / kN);
+    q[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[r].v[i] -= mean;
+      q[r] += x[r].v[i] * x[r].v[i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float rstd = rsqrtf(q[r] * (1.0f / kN) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[r].v[i] = x[r].v[i] * rstd * g.v[i] + b.v[i];
+  }
+}
+__device__ __forceinline__ void ln_row(f8& x, const f8& g, const f8& b, float eps) {
+  f8 (&one)[1] = reinterpret_cast<f8 (&)[1]>(x);
+  ln_rows<1>(one, g, b, eps);
 }
 
 // ---- optional per-kernel-class device timing (bench.py roofline leg; off by default) ----
@@ -230,6 +258,10 @@ int launch_gemm_tc_splitk(const bf16* A, int lda, const bf16* W, int ldw, float*
 // gemm_ln_tc.cu: C(bf16) = act(LN(R) W^T + bias), K = 256
 int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float* R,
                   int M, cudaStream_t st);
+// R += FFN(norm2(R)); H1 = norm1_next(R) (nullptr: not produced); scratch [M,256] bf16 receives norm2(R)
+int launch_ffn_tc_ln(float* R, const float* ln2_g, const float* ln2_b, float eps, bf16* scratch, const bf16* W1,
+                     const float* b1, const bf16* W2, const float* b2, const float* ln1n_g, const float* ln1n_b,
+                     bf16* H1, int M, cudaStream_t st);
 int launch_gemm_ln_tc(const float* R, const float* gamma, const float* beta, float eps, const bf16* W,
                       const float* bias, bf16* C, int ldc, int M, int N, int relu, cudaStream_t st);
 // attention.cu

@@ -29,6 +29,18 @@
 // adjacent row tiles: every weight box is fetched from L2 once per pair (each CTA loads 128 of the 256
 // rows and multicasts them).
 //
+// LNF variant (launch_ffn_tc_ln, 512 threads): the two LayerNorms either side of the sub-block ride along in this
+// compute-bound kernel instead of being two HBM-bound launches of their own (64 launches, 14.6 % of the cfg 2 forward):
+//   norm2 (CSE_transformer.py:406): warps 14-15 normalise the fp32 residual rows of the tiles AHEAD of the tensor pipe
+//     into a bf16 scratch matrix in global memory (it stays in L2) and the TMA producer loads the A tile from there once
+//     a shared-memory counter says the tile's rows are written (generic-proxy writes -> fence.proxy.async -> release /
+//     acquire -> TMA).  All fourteen non-pipe warps share the first tile so the pipe starts after two batches of rows.
+//   norm1 of the NEXT layer (CSE_transformer.py:387): each output warp owns 32 complete rows of the tile it has just
+//     folded into R; once its reduce-adds have completed it reads those rows back (L2 hits) and writes their LayerNorm
+//     for the next layer's in_proj GEMM.
+// A transformer layer is then four launches: in_proj GEMM, attention, out_proj GEMM (+R), this kernel.  The LNF tile
+// walk runs from the last row tile down: out_proj walked the rows upwards, so the walk starts in L2.
+//
 // Roles (448 threads): warp 0 TMA producer | warp 1 single-thread tcgen05.mma issuer | warps 2-9
 // hidden-chunk epilogue E1 (TMEM lane quarter = warp & 3, column half = (warp-2) >> 2) | warps 10-13
 // output epilogue Y -> R (one per lane quarter, two staging chunks each).  All mbarrier waits are bounded.
@@ -66,6 +78,9 @@ namespace {
 #endif
 
 constexpr int kFfnThreads = 448;
+// + warps 14-15: LayerNorm (norm2) producers.  Sixteen warps = four per SM sub-partition: a fifth warp on a
+// sub-partition would cap every thread at 96 registers and spill the E1 warps (the critical path)
+constexpr int kFfnLnThreads = 512;
 constexpr int kD = 256;        // d_model
 constexpr int kH = 1024;       // d_ffn
 constexpr int kHC = 256;       // hidden units per chunk
@@ -81,13 +96,80 @@ constexpr int kStgBytes = 32 * 128;     // output staging chunk: 32 rows x 32 fp
 constexpr int kBiasBytes = kD * 4;      // b2 (b1 is read through L1)
 constexpr size_t kFfnSmem = 1024 + kABytes + kStages * kStageBytes + 8 * kStgBytes + kBiasBytes + 256;
 
+struct FfnLn {            // LNF only
+  const float* R;         // [M,256] fp32 residual stream (also updated through tmR)
+  const float* g2;        // this layer's norm2 weight / bias
+  const float* b2;
+  const float* g1n;       // next layer's norm1 weight / bias (H1 == nullptr: not produced)
+  const float* b1n;
+  bf16* A;                // [M,256] scratch: norm2(R), written by the LayerNorm warps, read back through tmA
+  bf16* H1;               // [M,256] norm1_next(R + FFN(norm2(R)))
+  float eps;
+};
+
+__device__ __forceinline__ f8 ldcg8(const float* p) {  // L2 only: the rows are rewritten by TMA reduce-adds
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
+  f8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// LayerNorm of the eight rows [row0, row0 + 8) of R (clipped at M) -> bf16 rows of H.  One warp, 8 channels per lane
+// like layernorm_kernel (norm.cu: same arithmetic, same results); the eight rows' loads and reductions go together.
+__device__ __forceinline__ void ln_batch_bf16(const float* __restrict__ R, int M, int row0, const f8& gg, const f8& bb,
+                                              float eps, bf16* __restrict__ H, int lane) {
+  f8 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ldcg8(R + (size_t)min(row0 + i, M - 1) * kD + lane * 8);
+  ln_rows<8>(v, gg, bb, eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (row0 + i < M) st8(H + (size_t)(row0 + i) * kD + lane * 8, v[i]);
+}
+__device__ __forceinline__ void ln_rows_bf16(const float* __restrict__ R, int M, int row0, int nrows,
+                                             const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                             bf16* __restrict__ H, int lane) {
+  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);
+  for (int r = 0; r < nrows; r += 8) ln_batch_bf16(R, M, row0 + r, gg, bb, eps, H, lane);
+}
+// eight rows (8 KB, contiguous) -> L2, one instruction
+__device__ __forceinline__ void prefetch_rows8(const float* R, int M, int row0) {
+  if (row0 + 8 <= M)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(R + (size_t)row0 * kD), "r"(8 * kD * 4) : "memory");
+}
+
+// rows written (generic proxy) -> visible to the TMA producer's loads (async proxy): proxy fence, then a release
+// increment of the shared-memory row counter; the producer acquires it
+__device__ __forceinline__ void ln_signal(uint32_t ctr, int lane) {
+  asm volatile("fence.proxy.async;\n" ::: "memory");
+  __syncwarp();
+  if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;\n" ::"r"(ctr) : "memory");
+}
+__device__ __forceinline__ void ln_wait(uint32_t ctr, uint32_t target) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(ctr) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ffn_tc: LayerNorm rows timeout (block %d, have %u, need %u)\n", (int)blockIdx.x, v, target);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async;\n" ::: "memory");
+}
+
 // G2 consumes the four 64-unit pieces of a hidden chunk in the order E1 finishes them
 __device__ __forceinline__ int g2_piece(int s) { return s; }
 
-__global__ void __launch_bounds__(kFfnThreads, 1)
+template <bool LNF>
+__global__ void __launch_bounds__(LNF ? kFfnLnThreads : kFfnThreads, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmR,
-              const float* __restrict__ b1, const float* __restrict__ b2, int M) {
+              const float* __restrict__ b1, const float* __restrict__ b2, int M, FfnLn ln) {
+  constexpr int kThreads = LNF ? kFfnLnThreads : kFfnThreads;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -106,14 +188,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t bar_yfull = sBar + 200;
   const uint32_t bar_yempty = sBar + 208;
   const uint32_t tmem_slot = sBar + 216;
+  const uint32_t ln_ctr = sBar + 224;           // LNF: warps that have delivered their norm2 rows (14 for the first tile, 2 per later tile)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int m_pairs = ((M + 127) / 128 + 1) >> 1;
+  // tile pair of walk step i: LNF walks the row tiles downwards (see the header)
+  auto pair_at = [&](int i) { return LNF ? m_pairs - 1 - i : i; };
 
   if (threadIdx.x == 0) {
+    if constexpr (LNF) *reinterpret_cast<volatile uint32_t*>(smem_al + (ln_ctr - smem_base)) = 0u;
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
 #ifdef FFN_SOLO
@@ -133,7 +219,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     mbar_fence_init();
   }
   pdl_launch_dependents();
-  for (int i = threadIdx.x; i < kD; i += kFfnThreads) s_b2[i] = b2[i];  // parameter: not produced by the previous kernel
+  for (int i = threadIdx.x; i < kD; i += kThreads) s_b2[i] = b2[i];  // parameter: not produced by the previous kernel
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   fence_before();
   __syncthreads();
@@ -148,15 +234,17 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // ================= TMA producer (lane 0 acts; the warp stays convergent) =================
     uint32_t stage = 0, wphase = 0;
     int it = 0;
-    for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
+    for (int mpi = pair_id; mpi < m_pairs; mpi += npairs, ++it) {
+      const int mp = pair_at(mpi);
       const int m0 = (2 * mp + rank) * 128;
       if (lane == 0) {
-        if (mp + npairs < m_pairs) {  // next tile's A -> L2 while this tile computes
+        if (!LNF && mp + npairs < m_pairs) {  // next tile's A -> L2 while this tile computes
           for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, (2 * (mp + npairs) + rank) * 128);
         }
         for (int c = 0; c < kChunks; ++c) {
           for (int s = 0; s < 8; ++s) {  // stages 0..3: W1 k-blocks of G1_c; 4..7: W2 pieces of G2_c
             if (c == 0 && s < 4) {  // the previous tile's last G1 has finished with this k-block of A
+              if (LNF && s == 0) ln_wait(ln_ctr, 14u + 2u * (uint32_t)it);  // this tile's norm2 rows are written
               mbar_wait_spin(bar_aempty + 8 * s, ((uint32_t)it & 1u) ^ 1u, 1);
               mbar_expect_tx(bar_afull + 8 * s, kKb);
               tma_load_2d(sA + s * kKb, &tmA, bar_afull + 8 * s, s * 64, m0);
@@ -188,7 +276,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
     uint32_t stage = 0, wphase = 0;
     int it = 0;
-    for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
+    for (int mpi = pair_id; mpi < m_pairs; mpi += npairs, ++it) {
       if (lane == 0) {
         for (int c = 0; c < kChunks; ++c) {
           const uint32_t use = (uint32_t)(it * kChunks + c);
@@ -241,8 +329,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;            // TMEM lane quarter (fixed by hardware: warp id % 4)
     const int h = (warp - 2) >> 2;     // column half: hidden units [128h, 128h+128) of the chunk
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    if constexpr (LNF) {  // first tile: every non-pipe warp normalises eight of its rows
+      ln_rows_bf16(ln.R, M, (2 * pair_at(pair_id) + rank) * 128 + (warp - 2) * 8, 8, ln.g2, ln.b2, ln.eps, ln.A, lane);
+      ln_signal(ln_ctr, lane);
+    }
     int it = 0;
-    for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
+    for (int mpi = pair_id; mpi < m_pairs; mpi += npairs, ++it) {
       for (int c = 0; c < kChunks; ++c) {
         const uint32_t use = (uint32_t)(it * kChunks + c);
         mbar_wait(bar_hfull, use & 1u, 11);
@@ -292,15 +384,44 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
     }
+  } else if (LNF && warp >= 14) {
+    // ================= norm2 producers, warps 14..15 (LNF): rows of the tiles ahead -> bf16 scratch A =================
+    // first tile: rows [96, 128) (the E1 and output warps take eight rows each of [0, 96)); later tiles: 64 rows each.
+    // The warp's work is a stream of 8-row batches; the batch two places ahead is pulled into L2 while this one is
+    // normalised (a warp holds 8 KB of loads in registers — at HBM latency that is a third of the rate the tensor pipe
+    // consumes rows at; a whole tile of lead was too long: the lines were evicted again before use).
+    const f8 gg = ld8(ln.g2 + lane * 8), bb = ld8(ln.b2 + lane * 8);
+    const int w = warp - 14;
+    auto batch_row = [&](int mpi, int it, int b) {   // first row of batch b of walk step mpi
+      return (2 * pair_at(mpi) + rank) * 128 + (it == 0 ? 96 + w * 16 : w * 64) + b * 8;
+    };
+    int it = 0;
+    for (int mpi = pair_id; mpi < m_pairs; mpi += npairs, ++it) {
+      const int nb = it == 0 ? 2 : 8;
+      const bool more = mpi + npairs < m_pairs;
+      if (it == 0 && lane == 0) prefetch_rows8(ln.R, M, batch_row(mpi, 0, 1));
+      for (int b = 0; b < nb; ++b) {
+        if (lane == 0) {
+          if (b + 2 < nb) prefetch_rows8(ln.R, M, batch_row(mpi, it, b + 2));
+          else if (more) prefetch_rows8(ln.R, M, batch_row(mpi + npairs, it + 1, b + 2 - nb));
+        }
+        ln_batch_bf16(ln.R, M, batch_row(mpi, it, b), gg, bb, ln.eps, ln.A, lane);
+      }
+      ln_signal(ln_ctr, lane);
+    }
   } else {
     // ================= output epilogue Y + b2 -> R, warps 10..13 =================
     // fp32 residual stream updated in place by TMA reduce-add; rows past M are clipped by the tensor map
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t stg0 = sStg + (warp - 10) * 2 * kStgBytes;  // two staging chunks per warp
+    if constexpr (LNF) {
+      ln_rows_bf16(ln.R, M, (2 * pair_at(pair_id) + rank) * 128 + (warp - 2) * 8, 8, ln.g2, ln.b2, ln.eps, ln.A, lane);
+      ln_signal(ln_ctr, lane);
+    }
     int it = 0;
-    for (int mp = pair_id; mp < m_pairs; mp += npairs, ++it) {
-      const int row_base = (2 * mp + rank) * 128 + q * 32;
+    for (int mpi = pair_id; mpi < m_pairs; mpi += npairs, ++it) {
+      const int row_base = (2 * pair_at(mpi) + rank) * 128 + q * 32;
       mbar_wait(bar_yfull, (uint32_t)it & 1u, 13);
       fence_after();
       if (warp == 10 && lane == 0) { FFN_TRACE_PUT(2, it * 16); }
@@ -341,6 +462,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
 #endif
       }
+      if constexpr (LNF) {
+        if (ln.H1 != nullptr) {
+          // norm1 of the next layer on the 32 rows this warp has just updated: its own reduce-adds have completed
+          // (wait_group without .read), the rows come back from L2
+          if (lane == 0) {
+            bulk_wait_all();
+            asm volatile("fence.proxy.async;\n" ::: "memory");
+          }
+          __syncwarp();
+          ln_rows_bf16(ln.R, M, row_base, 32, ln.g1n, ln.b1n, ln.eps, ln.H1, lane);
+        }
+      }
     }
     if (lane == 0) bulk_wait_all();  // all residual updates complete before the CTA retires
     __syncwarp();
@@ -357,8 +490,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 }  // namespace
 
-int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float* R,
-                  int M, cudaStream_t st) {
+static int launch_ffn_common(bool lnf, const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2,
+                             float* R, int M, const FfnLn& ln, cudaStream_t st) {
   if (M <= 0) return 0;
   if (((uintptr_t)A | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)R | (uintptr_t)b1 | (uintptr_t)b2) & 15) {
     set_error("ffn_tc: operands must be 16-byte aligned");
@@ -366,7 +499,9 @@ int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2
   }
   static DeviceOnce once;
   if (!once.configured_on_this_device()) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfnSmem);
+    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ffn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfnSmem);
     if (e != cudaSuccess) {
       set_error("ffn_tc: cudaFuncSetAttribute(%zu B smem) failed: %s", kFfnSmem, cudaGetErrorString(e));
       return 1;
@@ -382,12 +517,37 @@ int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (m_pairs < max_pairs ? m_pairs : max_pairs);
   KernelScope prof(kClsGemmTc, st);
-  cudaError_t le = launch_pdl(ffn_tc_kernel, dim3(grid), dim3(kFfnThreads), kFfnSmem, st, 2, tmA, tmW1, tmW2, tmR, b1, b2, M);
+  cudaError_t le = lnf ? launch_pdl(ffn_tc_kernel<true>, dim3(grid), dim3(kFfnLnThreads), kFfnSmem, st, 2, tmA, tmW1,
+                                    tmW2, tmR, b1, b2, M, ln)
+                       : launch_pdl(ffn_tc_kernel<false>, dim3(grid), dim3(kFfnThreads), kFfnSmem, st, 2, tmA, tmW1,
+                                    tmW2, tmR, b1, b2, M, ln);
   if (le != cudaSuccess) {
     set_error("ffn_tc_kernel cluster launch failed: %s", cudaGetErrorString(le));
     return 1;
   }
   return check_launch("ffn_tc_kernel");
+}
+
+int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float* R,
+                  int M, cudaStream_t st) {
+  return launch_ffn_common(false, A, W1, b1, W2, b2, R, M, FfnLn{}, st);
+}
+
+// R += FFN(norm2(R)); H1 = norm1_next(R) (H1 == nullptr: not produced).  `scratch` [M,256] bf16 receives norm2(R).
+int launch_ffn_tc_ln(float* R, const float* ln2_g, const float* ln2_b, float eps, bf16* scratch, const bf16* W1,
+                     const float* b1, const bf16* W2, const float* b2, const float* ln1n_g, const float* ln1n_b,
+                     bf16* H1, int M, cudaStream_t st) {
+  if (((uintptr_t)ln2_g | (uintptr_t)ln2_b | (uintptr_t)ln1n_g | (uintptr_t)ln1n_b | (uintptr_t)H1) & 15) {
+    set_error("ffn_tc_ln: LayerNorm parameters / outputs must be 16-byte aligned");
+    return 1;
+  }
+  if (H1 != nullptr && (ln1n_g == nullptr || ln1n_b == nullptr)) {
+    set_error("ffn_tc_ln: H1 requested without the next layer's norm1 parameters");
+    return 1;
+  }
+  FfnLn ln;
+  ln.R = R; ln.g2 = ln2_g; ln.b2 = ln2_b; ln.g1n = ln1n_g; ln.b1n = ln1n_b; ln.A = scratch; ln.H1 = H1; ln.eps = eps;
+  return launch_ffn_common(true, scratch, W1, b1, W2, b2, R, M, ln, st);
 }
 
 }  // namespace cse

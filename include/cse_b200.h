@@ -221,6 +221,17 @@ CSE_API int cse_linear(const void* A, int lda, const void* W, const float* bias,
 CSE_API int cse_ffn_fused(const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                           const float* b2, float* R, int M, void* stream);
 
+/* The feed-forward sub-block WITH the LayerNorms either side of it (CSE_transformer.py:406-411 of this layer, :387 of
+ * the next one), CSE_BF16 only:
+ *   A = LayerNorm(R; ln2_g, ln2_b, eps) (bf16, left in `scratch_bf16` [M,256]);
+ *   R[M,256] (fp32, in place) += relu(A W1^T + b1) W2^T + b2;
+ *   H1[M,256] (bf16) = LayerNorm(R_new; next_ln1_g, next_ln1_b, eps)       (H1_bf16 == NULL: not produced)
+ * norm2 runs in dedicated warps ahead of the tensor pipe, the next layer's norm1 in the output warps on the rows they
+ * have just updated: a transformer layer is four launches (in_proj, attention, out_proj, this). */
+CSE_API int cse_ffn_ln_fused(float* R, const float* ln2_g, const float* ln2_b, float eps, void* scratch_bf16,
+                             const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                             const float* next_ln1_g, const float* next_ln1_b, void* H1_bf16, int M, void* stream);
+
 /* Attention output projection + residual add + pre-FFN LayerNorm in one tcgen05 kernel (CSE_transformer.py:399-408:
  * `src = src + self_att(...)` then `norm2(src)`), CSE_BF16 only:
  *   R[M,256] (fp32, in place) += A[M,K] W[256,K]^T + bias;   H[M,256] (bf16) = LayerNorm(R; gamma, beta, eps)

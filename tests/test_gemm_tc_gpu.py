@@ -131,6 +131,54 @@ def test_ffn_fused(M):
     assert rel_l2(Rd.cpu(), R2.double().cpu()) < 5e-5
 
 
+@pytest.mark.parametrize("M", [1, 128, 129, 517, 20000, 2 * 148 * 128 + 77, 3 * 148 * 128 + 5])
+@pytest.mark.parametrize("with_next", [True, False])
+def test_ffn_ln_fused(M, with_next):
+    """cse_ffn_ln_fused == layernorm_kernel (norm2) -> cse_ffn_fused -> layernorm_kernel (next layer's norm1)
+    (CSE_transformer.py:406-411 and :387 of the following layer).  The LayerNorm warps run layernorm_kernel's
+    arithmetic and the GEMMs see the same operands, so the three results are BIT-EXACT with the three-launch path;
+    the float64 check guards that path itself."""
+    W1 = (_rand(1024, 256, seed=22) / 16).to(torch.bfloat16).to(DEV)
+    W2 = (_rand(256, 1024, seed=23) / 32).to(torch.bfloat16).to(DEV)
+    b1, b2 = _rand(1024, seed=24).to(DEV), _rand(256, seed=25).to(DEV)
+    g2, be2 = (1 + 0.1 * _rand(256, seed=27)).to(DEV), (0.1 * _rand(256, seed=28)).to(DEV)
+    g1, be1 = (1 + 0.1 * _rand(256, seed=29)).to(DEV), (0.1 * _rand(256, seed=30)).to(DEV)
+    R0 = (_rand(M, 256, seed=26) * 1.5 + 0.25).to(DEV)
+
+    # three-launch path
+    A_ref = torch.empty(M, 256, dtype=torch.bfloat16, device=DEV)
+    R_ref = R0.clone()
+    H_ref = torch.empty(M, 256, dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_layernorm_fwd", _lib.ptr(R_ref), _lib.ptr(g2), _lib.ptr(be2), M, 1e-6, BF16, _lib.ptr(A_ref), _st())
+    _lib.call("cse_ffn_fused", _lib.ptr(A_ref), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2),
+              _lib.ptr(R_ref), M, _st())
+    _lib.call("cse_layernorm_fwd", _lib.ptr(R_ref), _lib.ptr(g1), _lib.ptr(be1), M, 1e-6, BF16, _lib.ptr(H_ref), _st())
+
+    R = R0.clone()
+    A = torch.full((M, 256), float("nan"), dtype=torch.bfloat16, device=DEV)
+    H = torch.full((M, 256), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.call("cse_ffn_ln_fused", _lib.ptr(R), _lib.ptr(g2), _lib.ptr(be2), 1e-6, _lib.ptr(A), _lib.ptr(W1),
+              _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(g1) if with_next else None,
+              _lib.ptr(be1) if with_next else None, _lib.ptr(H) if with_next else None, M, _st())
+    torch.cuda.synchronize()
+    assert torch.equal(A, A_ref)
+    assert torch.equal(R, R_ref)
+    if with_next:
+        assert torch.equal(H, H_ref)
+    else:
+        assert torch.isnan(H.float()).all()
+
+    x = R0.double().cpu()
+    ln = lambda t, g, b: (t - t.mean(-1, keepdim=True)) / torch.sqrt(t.var(-1, unbiased=False, keepdim=True) + 1e-6) \
+        * g.double().cpu() + b.double().cpu()  # noqa: E731
+    a = ln(x, g2, be2).float().to(torch.bfloat16).double()
+    hid = torch.relu(a @ W1.double().cpu().t() + b1.double().cpu()).float().to(torch.bfloat16).double()
+    ref = x + hid @ W2.double().cpu().t() + b2.double().cpu()
+    assert rel_l2(R.cpu(), ref) < 3e-4     # a LayerNorm output within rounding error of a bf16 boundary flips one ulp
+    if with_next:
+        assert rel_l2(H.float().cpu(), ln(R.double().cpu(), g1, be1)) < 3e-3
+
+
 def test_gemm_tc_strided_views():
     """conv2d output [B*L, spk*256] re-read as [B*L*spk, 256] (abi.cu masknet_impl) and lda > K."""
     M, K = 777, 256
