@@ -207,13 +207,14 @@ static bool outproj_ln_fused_enabled() {
 // The two LayerNorms of a layer ride along in the feed-forward kernel (ffn_tc.cu, LNF variant): norm2 in its own
 // LayerNorm warps ahead of the tensor pipe, norm1 of the NEXT layer in its output warps — four launches per layer.
 // CSE_FFN_LN=0 keeps the separate layernorm_kernel launches (A/B aid).
-static bool ffn_ln_fused_enabled() {
-  static const bool on = []() {
+static int ffn_ln_mode() {   // 0: off, 1: norm2 + next norm1 (default), 2: norm2 only (norm1 stays a launch)
+  static const int mode = []() {
     const char* e = getenv("CSE_FFN_LN");
-    return e == nullptr || e[0] != '0';
+    return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }();
-  return on;
+  return mode;
 }
+static bool ffn_ln_fused_enabled() { return ffn_ln_mode() != 0; }
 
 // CSE_LN_FUSED=1 runs norm1 -> in_proj as one kernel (gemm_ln_tc.cu).  Off by default: measured 123-132 us
 // against 36 + 67 us for the two kernels (its LayerNorm warps cannot keep enough loads in flight inside the
@@ -241,7 +242,7 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
                       !ln_qkv_fused_enabled() && !outproj_ln_fused_enabled();
   for (int l = 0; l < CSE_LAYERS; ++l) {
     const cse_layer_params& lp = sp.layer[l];
-    if (ffn_ln && l > 0) {
+    if (ffn_ln && l > 0 && ffn_ln_mode() == 1) {
       // norm1(R) is already in H: the previous layer's feed-forward kernel wrote it
       if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
                  3 * kN, kN, 0, 0, st)) return 1;
@@ -270,7 +271,7 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
       // norm2 -> Linear -> ReLU -> Linear -> +R -> next layer's norm1, one kernel; AO (consumed by out_proj) is the
       // scratch that receives norm2(R)
       CSE_REQUIRE(lp.ffn1_w_bf16 && lp.ffn2_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
-      const cse_layer_params* nx = l + 1 < CSE_LAYERS ? &sp.layer[l + 1] : nullptr;
+      const cse_layer_params* nx = l + 1 < CSE_LAYERS && ffn_ln_mode() == 1 ? &sp.layer[l + 1] : nullptr;
       if (launch_ffn_tc_ln(R, lp.ln2_g, lp.ln2_b, 1e-6f, (bf16*)AO, (const bf16*)lp.ffn1_w_bf16, lp.ffn1_b,
                            (const bf16*)lp.ffn2_w_bf16, lp.ffn2_b, nx ? nx->ln1_g : nullptr,
                            nx ? nx->ln1_b : nullptr, nx ? (bf16*)H : nullptr, M, st)) return 1;

@@ -150,8 +150,10 @@ int cse_layer_fwd(const cse_layer_params* p, float* R, int nseq, int n, int prec
   if (launch_gemm_tc(H, kN, (const bf16*)p->in_proj_w_bf16, p->in_proj_b, 1.f, nullptr, QKV, 3 * kN, Mi, 3 * kN, kN, 0, 0, st)) return 1;
   if (launch_attention(QKV, nseq, n, CSE_BF16, AO, st)) return 1;
   if (launch_gemm_tc(AO, kN, (const bf16*)p->out_proj_w_bf16, p->out_proj_b, 1.f, R, R, kN, Mi, kN, kN, 0, 1, st)) return 1;
-  if (launch_layernorm(R, p->ln2_g, p->ln2_b, Mi, 1e-6f, CSE_BF16, H, st)) return 1;
-  return launch_ffn_tc(H, (const bf16*)p->ffn1_w_bf16, p->ffn1_b, (const bf16*)p->ffn2_w_bf16, p->ffn2_b, R, Mi, st);
+  // norm2 rides along in the feed-forward kernel's LayerNorm warps (ffn_tc.cu; H receives norm2(R)) — same results as
+  // layernorm_kernel + launch_ffn_tc
+  return launch_ffn_tc_ln(R, p->ln2_g, p->ln2_b, 1e-6f, H, (const bf16*)p->ffn1_w_bf16, p->ffn1_b,
+                          (const bf16*)p->ffn2_w_bf16, p->ffn2_b, nullptr, nullptr, nullptr, Mi, st);
 }
 
 int cse_layer_bwd(const cse_layer_params* p, const cse_layer_grads* g, const float* R_in, float* dR,

@@ -79,6 +79,36 @@ __device__ __forceinline__ void st8(bf16* p, const f8& r) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Row access for one-warp-per-row kernels over 256 channels: lane L owns channels [4L, 4L + 4) and [128 + 4L, +4), so
+// each of the two 16-byte accesses of a row is one contiguous 512-byte request (with 8 consecutive channels per lane
+// both accesses touch all 32 sectors of the row and use half of each).  `row` points at the row's first channel.
+__device__ __forceinline__ f8 ld_row8(const float* row, int lane) {
+  const float4 a = reinterpret_cast<const float4*>(row)[lane];
+  const float4 b = reinterpret_cast<const float4*>(row)[32 + lane];
+  f8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ f8 ld_row8_cg(const float* row, int lane) {  // L2 only (rows another proxy rewrites)
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(row) + lane);
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(row) + 32 + lane);
+  f8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_row8(float* row, int lane, const f8& r) {
+  reinterpret_cast<float4*>(row)[lane] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  reinterpret_cast<float4*>(row)[32 + lane] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void st_row8(bf16* row, int lane, const f8& r) {
+  __nv_bfloat162 lo[2] = {__floats2bfloat162_rn(r.v[0], r.v[1]), __floats2bfloat162_rn(r.v[2], r.v[3])};
+  __nv_bfloat162 hi[2] = {__floats2bfloat162_rn(r.v[4], r.v[5]), __floats2bfloat162_rn(r.v[6], r.v[7])};
+  reinterpret_cast<uint2*>(row)[lane] = *reinterpret_cast<const uint2*>(lo);
+  reinterpret_cast<uint2*>(row)[32 + lane] = *reinterpret_cast<const uint2*>(hi);
+}
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

@@ -105,33 +105,32 @@ struct FfnLn {            // LNF only
   bf16* A;                // [M,256] scratch: norm2(R), written by the LayerNorm warps, read back through tmA
   bf16* H1;               // [M,256] norm1_next(R + FFN(norm2(R)))
   float eps;
+  int dbg;                // timing experiments only (cse_debug_ffn_ln): 1 = norm2 warps skip their rows, 2 = no norm1
 };
+int g_ffn_ln_dbg = 0;
+// dbg & 4: block 0 stamps clock64 per tile — [4 it + k]: output warp 10 (k = 0 Y ready, 1 Y drained, 2 reduce-adds
+// complete, 3 norm1 rows written); [128 + it]: norm2 warp 14 delivered tile it; [160 + it]: the producer got tile it's rows
+__device__ unsigned long long g_ffn_ln_trace[192];
+#define LN_STAMP(cond, idx) \
+  if ((ln.dbg & 4) && blockIdx.x == 0 && lane == 0 && (cond) && (idx) < 192) g_ffn_ln_trace[idx] = clock64()
 
-__device__ __forceinline__ f8 ldcg8(const float* p) {  // L2 only: the rows are rewritten by TMA reduce-adds
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
-  f8 r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-
-// LayerNorm of the eight rows [row0, row0 + 8) of R (clipped at M) -> bf16 rows of H.  One warp, 8 channels per lane
-// like layernorm_kernel (norm.cu: same arithmetic, same results); the eight rows' loads and reductions go together.
+// LayerNorm of the eight rows [row0, row0 + 8) of R (clipped at M) -> bf16 rows of H.  One warp, layernorm_kernel's
+// arithmetic and channel ownership (norm.cu: same results); the eight rows' loads and reductions go together.  Loads go
+// to L2 only: the rows are rewritten by TMA reduce-adds.
 __device__ __forceinline__ void ln_batch_bf16(const float* __restrict__ R, int M, int row0, const f8& gg, const f8& bb,
                                               float eps, bf16* __restrict__ H, int lane) {
   f8 v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = ldcg8(R + (size_t)min(row0 + i, M - 1) * kD + lane * 8);
+  for (int i = 0; i < 8; ++i) v[i] = ld_row8_cg(R + (size_t)min(row0 + i, M - 1) * kD, lane);
   ln_rows<8>(v, gg, bb, eps);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    if (row0 + i < M) st8(H + (size_t)(row0 + i) * kD + lane * 8, v[i]);
+    if (row0 + i < M) st_row8(H + (size_t)(row0 + i) * kD, lane, v[i]);
 }
 __device__ __forceinline__ void ln_rows_bf16(const float* __restrict__ R, int M, int row0, int nrows,
                                              const float* __restrict__ g, const float* __restrict__ b, float eps,
                                              bf16* __restrict__ H, int lane) {
-  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);
+  const f8 gg = ld_row8(g, lane), bb = ld_row8(b, lane);
   for (int r = 0; r < nrows; r += 8) ln_batch_bf16(R, M, row0 + r, gg, bb, eps, H, lane);
 }
 // eight rows (8 KB, contiguous) -> L2, one instruction
@@ -158,7 +157,6 @@ __device__ __forceinline__ void ln_wait(uint32_t ctr, uint32_t target) {
       __trap();
     }
   }
-  asm volatile("fence.proxy.async;\n" ::: "memory");
 }
 
 // G2 consumes the four 64-unit pieces of a hidden chunk in the order E1 finishes them
@@ -244,7 +242,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int c = 0; c < kChunks; ++c) {
           for (int s = 0; s < 8; ++s) {  // stages 0..3: W1 k-blocks of G1_c; 4..7: W2 pieces of G2_c
             if (c == 0 && s < 4) {  // the previous tile's last G1 has finished with this k-block of A
-              if (LNF && s == 0) ln_wait(ln_ctr, 14u + 2u * (uint32_t)it);  // this tile's norm2 rows are written
+              if (LNF && s == 0) {
+                ln_wait(ln_ctr, 14u + 2u * (uint32_t)it);  // this tile's norm2 rows are written
+                LN_STAMP(it < 32, 160 + it);
+              }
               mbar_wait_spin(bar_aempty + 8 * s, ((uint32_t)it & 1u) ^ 1u, 1);
               mbar_expect_tx(bar_afull + 8 * s, kKb);
               tma_load_2d(sA + s * kKb, &tmA, bar_afull + 8 * s, s * 64, m0);
@@ -356,6 +357,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const float4* bsrc = reinterpret_cast<const float4*>(b1 + c * kHC + p * 64 + h * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) bq[i] = __ldg(bsrc + i);  // lane-uniform, L1-resident
+          if constexpr (LNF) {
+            if (ln.dbg & 8) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bq[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // timing experiment: no bias loads
+            }
+          }
           float v[32];
           tmem_ld32(tmem_h + lane_off + p * 64 + h * 32, v);
           E1_STAMP(0)
@@ -390,7 +397,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // The warp's work is a stream of 8-row batches; the batch two places ahead is pulled into L2 while this one is
     // normalised (a warp holds 8 KB of loads in registers — at HBM latency that is a third of the rate the tensor pipe
     // consumes rows at; a whole tile of lead was too long: the lines were evicted again before use).
-    const f8 gg = ld8(ln.g2 + lane * 8), bb = ld8(ln.b2 + lane * 8);
+    const f8 gg = ld_row8(ln.g2, lane), bb = ld_row8(ln.b2, lane);
     const int w = warp - 14;
     auto batch_row = [&](int mpi, int it, int b) {   // first row of batch b of walk step mpi
       return (2 * pair_at(mpi) + rank) * 128 + (it == 0 ? 96 + w * 16 : w * 64) + b * 8;
@@ -405,9 +412,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (b + 2 < nb) prefetch_rows8(ln.R, M, batch_row(mpi, it, b + 2));
           else if (more) prefetch_rows8(ln.R, M, batch_row(mpi + npairs, it + 1, b + 2 - nb));
         }
-        ln_batch_bf16(ln.R, M, batch_row(mpi, it, b), gg, bb, ln.eps, ln.A, lane);
+        if (!(ln.dbg & 1)) ln_batch_bf16(ln.R, M, batch_row(mpi, it, b), gg, bb, ln.eps, ln.A, lane);
       }
       ln_signal(ln_ctr, lane);
+      LN_STAMP(warp == 14 && it < 32, 128 + it);
     }
   } else {
     // ================= output epilogue Y + b2 -> R, warps 10..13 =================
@@ -424,6 +432,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int row_base = (2 * pair_at(mpi) + rank) * 128 + q * 32;
       mbar_wait(bar_yfull, (uint32_t)it & 1u, 13);
       fence_after();
+      if constexpr (LNF) { LN_STAMP(warp == 10 && it < 32, 4 * it); }
       if (warp == 10 && lane == 0) { FFN_TRACE_PUT(2, it * 16); }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -463,15 +472,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #endif
       }
       if constexpr (LNF) {
-        if (ln.H1 != nullptr) {
+        LN_STAMP(warp == 10 && it < 32, 4 * it + 1);
+        if (ln.H1 != nullptr && !(ln.dbg & 2)) {
           // norm1 of the next layer on the 32 rows this warp has just updated: its own reduce-adds have completed
           // (wait_group without .read), the rows come back from L2
           if (lane == 0) {
-            bulk_wait_all();
-            asm volatile("fence.proxy.async;\n" ::: "memory");
+            if (ln.dbg & 16) bulk_wait_read<0>();   // timing experiment: no L1 invalidate (rows may be stale)
+            else bulk_wait_all();   // completion of the writes; includes the L1 invalidate generic loads need
           }
           __syncwarp();
+          LN_STAMP(warp == 10 && it < 32, 4 * it + 2);
           ln_rows_bf16(ln.R, M, row_base, 32, ln.g1n, ln.b1n, ln.eps, ln.H1, lane);
+          LN_STAMP(warp == 10 && it < 32, 4 * it + 3);
         }
       }
     }
@@ -528,6 +540,11 @@ static int launch_ffn_common(bool lnf, const bf16* A, const bf16* W1, const floa
   return check_launch("ffn_tc_kernel");
 }
 
+extern "C" __attribute__((visibility("default"))) void cse_debug_ffn_ln(int flags) { g_ffn_ln_dbg = flags; }
+extern "C" __attribute__((visibility("default"))) int cse_debug_ffn_ln_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_ffn_ln_trace, sizeof(g_ffn_ln_trace));
+}
+
 int launch_ffn_tc(const bf16* A, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float* R,
                   int M, cudaStream_t st) {
   return launch_ffn_common(false, A, W1, b1, W2, b2, R, M, FfnLn{}, st);
@@ -546,6 +563,7 @@ int launch_ffn_tc_ln(float* R, const float* ln2_g, const float* ln2_b, float eps
     return 1;
   }
   FfnLn ln;
+  ln.dbg = g_ffn_ln_dbg;
   ln.R = R; ln.g2 = ln2_g; ln.b2 = ln2_b; ln.g1n = ln1n_g; ln.b1n = ln1n_b; ln.A = scratch; ln.H1 = H1; ln.eps = eps;
   return launch_ffn_common(true, scratch, W1, b1, W2, b2, R, M, ln, st);
 }

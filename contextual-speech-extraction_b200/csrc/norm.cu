@@ -9,7 +9,7 @@
 
 namespace cse {
 
-// One warp per row of 256 fp32 channels (1 KB): 8 channels per lane, two shuffles trees.
+// One warp per row of 256 fp32 channels (1 KB): 8 channels per lane (ld_row8's split ownership), two shuffle trees.
 // Algorithmic bytes per row: 1024 in + e*256 out.
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x,
@@ -20,15 +20,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * 8;
-  const f8 gg = ld8(g + lane * 8), bb = ld8(b + lane * 8);  // parameters: not produced by the previous kernel
+  const f8 gg = ld_row8(g, lane), bb = ld_row8(b, lane);  // parameters: not produced by the previous kernel
   pdl_wait();
   for (size_t rr = warp; rr < M; rr += nwarps) {
     // reverse: sweep from the last row down, i.e. start with the rows the producer of x (a GEMM that walks
     // the rows upwards) touched last and that are still in L2
     const size_t r = reverse ? M - 1 - rr : rr;
-    f8 v = ld8(x + r * kN + lane * 8);
+    f8 v = ld_row8(x + r * kN, lane);
     ln_row(v, gg, bb, eps);
-    st8(out + r * kN + lane * 8, v);
+    st_row8(out + r * kN, lane, v);
   }
 }
 
