@@ -675,6 +675,24 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     n0 = lib.cse_launch_count()
     loss0 = step_device()
     launches = lib.cse_launch_count() - n0
+    loss0 = float(loss0.item())
+    # One process, fused optimiser: the whole step (forward, loss, backward, clip + AdamW) replays as ONE CUDA graph
+    # (runtime.GraphedStep) — run eagerly its ~1000 short launches are bound by the launching host thread.  A
+    # DistributedDataParallel step (N > 1) stays eager.
+    graphed = None
+    if world == 1 and fused_opt and args.train_graph != "off":
+        from cse_b200.runtime import GraphedStep
+        graphed = GraphedStep(lambda m, c, t: step(m, c, t), mix_d, ctx_d, tgt_d, warmup=3)
+
+        def step_device():                                                   # noqa: F811
+            return graphed(mix_d, ctx_d, tgt_d)
+
+        def step_host():                                                     # noqa: F811
+            return graphed(mix_h, ctx_h, tgt_h).item()                       # H2D into the static inputs, replay, D2H of the loss
+
+        for _ in range(2):
+            step_device()
+        torch.cuda.synchronize()
     ms_total, _ = timed(step_device, steps, sample_clocks=True)
     ms_step = ms_total / steps
     audio_s = TRAIN_BATCH * (Tt / SR) * world
@@ -723,7 +741,9 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
                    "precision": "torch.autocast(bfloat16): bf16 tensor-core transformer layers, fp32 elsewhere" if amp else "fp32",
                    "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
                    "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
-        "clocks": clocks, "loss": float(loss0.item()), "n_params": n_params, "comm": comm,
+        "clocks": clocks, "loss": loss0, "n_params": n_params, "comm": comm,
+        "step_execution": ("one CUDA graph replay per step (cse_b200.runtime.GraphedStep)" if graphed is not None
+                           else "eager launches (DistributedDataParallel step)" if world > 1 else "eager launches"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() + ctx_h.numel() + tgt_h.numel()) * 4,
                 "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
         "gpu_launches": int(launches), "roofline": roofline,
@@ -773,6 +793,8 @@ def main():
                     help="training leg: torch.autocast(bf16) like the reference's --bf16 (tensor-core layers), or the fp32 parity kernels")
     ap.add_argument("--train-ragged", action="store_true",
                     help="training leg: DailyTalk-like lengths U(1.5 s, 8 s) right-padded to the batch max instead of fixed --train-seconds")
+    ap.add_argument("--train-graph", default="auto", choices=["auto", "off"],
+                    help="training leg at N = 1: replay the whole step as one CUDA graph (auto) or launch it eagerly (off)")
     ap.add_argument("--no-train", action="store_true", help="forward workload: skip the `train` sub-object")
     ap.add_argument("--ddp-bucket-view", action="store_true", help="training leg, N > 1: DDP(gradient_as_bucket_view=True) (A/B; the reference uses the defaults)")
     ap.add_argument("--ddp-bucket-mb", type=int, default=0, help="training leg, N > 1: DDP(bucket_cap_mb=...) (A/B; default 25)")

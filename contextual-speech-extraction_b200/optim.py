@@ -80,7 +80,8 @@ class AdamW(torch.optim.Optimizer):
             arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
             sts = [self._moments(p, amsgrad) for p in ps]
             n_chunks = _lib.load().cse_optim_chunk_count(n, numel)
-            hosts = [torch.empty(n_chunks * 48, dtype=torch.uint8).pin_memory() for _ in range(4)]
+            # four rotating staging copies for eager steps + one owned by a captured step (CUDA graph)
+            hosts = [torch.empty(n_chunks * 48, dtype=torch.uint8).pin_memory() for _ in range(5)]
             garr = (C.c_void_p * n)(*gptrs)
             for h in hosts:
                 _lib.call("cse_optim_table_fill", n, numel, arr(ps), garr, arr([s["exp_avg"] for s in sts]),
@@ -91,9 +92,23 @@ class AdamW(torch.optim.Optimizer):
             for t in (ps[0].grad, ps[-1].grad):
                 self._check(t, "gradient")
             d.update(key=static_key, gptrs=None, numel=numel, n_chunks=n_chunks, hosts=hosts, turn=0,
-                     events=[None] * 4,
+                     events=[None] * 4, graph_gptrs=None,
                      table=torch.empty(n_chunks * 48, dtype=torch.uint8, device=dev),
+                     graph_table=torch.empty(n_chunks * 48, dtype=torch.uint8, device=dev),
                      partial=torch.empty(n_chunks, dtype=torch.float32, device=dev))
+        if torch.cuda.is_current_stream_capturing():
+            # A captured step (runtime.GraphedStep): its gradients live at fixed addresses in the graph's pool.  The
+            # upload becomes a node of the graph and re-reads ITS OWN pinned copy and device table on every replay, so
+            # eager steps of the same optimiser (which rotate the other four copies) cannot disturb it.
+            if d["graph_gptrs"] is not None and d["graph_gptrs"] != gptrs:
+                raise _lib.CseError("AdamW: one captured step per optimiser (gradient addresses differ from the "
+                                    "captured ones)")
+            h = d["hosts"][4]
+            _lib.call("cse_optim_table_set_grads", n, d["numel"], (C.c_void_p * n)(*gptrs), C.c_void_p(h.data_ptr()),
+                      h.numel())
+            d["graph_table"].copy_(h, non_blocking=True)
+            d["graph_gptrs"] = gptrs
+            return d["graph_table"]
         if d["gptrs"] != gptrs:
             slot = d["turn"] & 3
             d["turn"] += 1
@@ -107,6 +122,7 @@ class AdamW(torch.optim.Optimizer):
             ev.record()
             d["events"][slot] = ev
             d["gptrs"] = gptrs
+        return d["table"]
 
     # ---- the update --------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -124,10 +140,10 @@ class AdamW(torch.optim.Optimizer):
             if not ps[0].is_cuda:
                 raise _lib.CseError(f"parameter is on {ps[0].device}: the CUDA path has no CPU fallback")
             d = self._group_dev(gi, ps[0].device)
-            self._table(d, ps, bool(group["amsgrad"]))
+            table = self._table(d, ps, bool(group["amsgrad"]))
             _, gf, bf, gint = self._scaler
             b1, b2 = group["betas"]
-            _lib.call("cse_optim_step", _lib.ptr(d["table"]), d["n_chunks"], float(group["lr"]), float(b1), float(b2),
+            _lib.call("cse_optim_step", _lib.ptr(table), d["n_chunks"], float(group["lr"]), float(b1), float(b2),
                       float(group["eps"]), float(group["weight_decay"]), int(bool(group["amsgrad"])),
                       float(max_norm) if max_norm is not None else 0.0, int(self._use_scaler), gf, bf, gint,
                       int(bool(write_back_grads)), _lib.ptr(d["state"]), _lib.ptr(d["partial"]),

@@ -32,6 +32,52 @@ def resolve_precision(explicit=None):
     return BF16 if torch.is_autocast_enabled() else FP32
 
 
+class GraphedStep:
+    """A whole training step — `fn(*static_args)`: forward, loss, backward, clip + optimiser — captured into ONE CUDA
+    graph and replayed.  The autocast step of BASELINE configs[2] is ~1000 launches of 5-25 us each, so run eagerly it
+    is bound by the launching host thread (18-33 ms on a shared box); replayed it runs at the GPU's pace.
+
+        opt = AdamW(model.parameters(), lr=1e-4, amsgrad=True)
+        def step(mix, ctx, tgt):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = -si_snr(model(mix, ctx)[:, :, 0], tgt)
+            loss.backward()
+            opt.step(max_norm=5.0)
+            return loss
+        graphed = GraphedStep(step, mix_static, ctx_static, tgt_static)
+        loss = graphed(mix, ctx, tgt)         # copies the arguments into the static tensors, replays
+
+    Requirements (the usual ones of torch.cuda.graph): fixed shapes, no host synchronisation inside `fn`, the fused
+    optimiser of this package (or a capturable torch optimiser); `fn` runs `warmup` times eagerly first.  Single
+    process per graph: a DistributedDataParallel step is not captured here."""
+
+    def __init__(self, fn, *static_args, warmup=3):
+        self.args = static_args
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*static_args)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(*static_args)
+
+    def __call__(self, *args):
+        if len(args) != len(self.args):
+            raise ValueError(f"GraphedStep: expected {len(self.args)} arguments, got {len(args)}")
+        for dst, src in zip(self.args, args):
+            if src is not dst:
+                if src.shape != dst.shape or src.dtype != dst.dtype:
+                    raise _lib.CseError(f"GraphedStep: argument {tuple(src.shape)} {src.dtype} does not match the "
+                                        f"captured {tuple(dst.shape)} {dst.dtype}")
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class ParamTable:
     """Builds the `cse_params` struct from a module's state and keeps the bf16 pack fresh."""
 

@@ -340,3 +340,50 @@ def test_autocast_training_step_carries_a_graph_and_stays_within_reference_drift
     assert all(torch.isfinite(g).all() for g in got.values())
     assert drift <= bar
     assert abs(loss.item() - ref_loss) <= max(0.05, 1.5 * abs(float(fix["bf16_ref_loss"]) - float(fix["loss"])))
+
+
+def test_graphed_training_step_matches_eager_steps():
+    """runtime.GraphedStep: the autocast step (forward, -SI-SNR, backward, clip + fused AdamW) replayed as one CUDA
+    graph follows the same trajectory as eagerly launched steps (train_ContExt.py:365-389).  Same kernels, same
+    inputs; the only run-to-run difference is the order of the split-K reduce-adds of the weight gradients."""
+    from cse_b200.optim import AdamW
+    from cse_b200.runtime import GraphedStep
+    sd, mix, src, ctx, se, meta = model_case("context_2spk_b2_t3000")
+    mix_d, ctx_d, tgt_d = mix.to(DEV), ctx.to(DEV), src[:, :, 0].contiguous().to(DEV)
+    sisnr = losses.ScaleInvariantSignalNoiseRatio()
+
+    def make():
+        m = build_model(meta)
+        m.load_state_dict(sd)
+        m = m.to(DEV).train()
+        opt = AdamW(m.parameters(), lr=1e-3, amsgrad=True)
+
+        def step(mx, cx, tg):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = -sisnr(m(mx, cx)[:, :, 0], tg)
+            loss.backward()
+            opt.step(max_norm=5.0)
+            return loss
+        return m, opt, step
+
+    m_e, opt_e, step_e = make()
+    eager_losses = [step_e(mix_d, ctx_d, tgt_d).item() for _ in range(6)]
+
+    m_g, opt_g, step_g = make()
+    graphed = GraphedStep(step_g, mix_d.clone(), ctx_d.clone(), tgt_d.clone(), warmup=3)   # three eager steps, then the capture
+    graph_losses = [graphed(mix_d, ctx_d, tgt_d).item() for _ in range(3)]                 # steps 4-6
+    torch.cuda.synchronize()
+    assert opt_g.steps_applied() == 6 and opt_e.steps_applied() == 6
+    assert all(abs(a - b) <= 2e-2 * max(1.0, abs(b)) for a, b in zip(graph_losses, eager_losses[3:])), (graph_losses, eager_losses)
+    assert eager_losses[-1] < eager_losses[0]                      # the steps do train
+    num = sum(((pg.detach() - pe.detach()).double() ** 2).sum() for pg, pe in zip(m_g.parameters(), m_e.parameters()))
+    den = sum((pe.detach().double() ** 2).sum() for pe in m_e.parameters())
+    assert (num / den).sqrt().item() < 2e-3
+    # an eager step of the same optimiser after the capture still works (its own staging copies and device table)
+    before = opt_g.steps_applied()
+    step_g(mix_d, ctx_d, tgt_d)
+    graphed(mix_d, ctx_d, tgt_d)
+    torch.cuda.synchronize()
+    assert opt_g.steps_applied() == before + 2
+    assert all(torch.isfinite(p).all() for p in m_g.parameters())
