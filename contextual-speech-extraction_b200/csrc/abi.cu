@@ -227,22 +227,27 @@ static bool ln_qkv_fused_enabled() {
   return on;
 }
 
+static bool ffn_ln_path(const Plan& pl) {
+  return pl.precision == CSE_BF16 && ffn_fused_enabled() && ffn_ln_fused_enabled() && !ln_qkv_fused_enabled() &&
+         !outproj_ln_fused_enabled();
+}
+
 // SBTransformerBlock_CSE body after the PE add: 8 pre-norm layers on the fp32 residual stream R
 // (TransformerEncoderLayer.forward, CSE_transformer.py:385-416).  The final LayerNorm belongs to
 // the stack tail (stack_finish / pred_head).
+// h_ready: norm1 of the first layer is already in ws+H (written by the kernel that built R: build_seq / stack tail)
 static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int nseq, int n,
-                     char* ws, cudaStream_t st) {
+                     char* ws, cudaStream_t st, bool h_ready = false) {
   const int M = nseq * n;
   void* H = ws + pl.H;
   void* QKV = ws + pl.QKV;
   void* AO = ws + pl.AO;
   void* F1 = ws + pl.F1;
   const int act = pl.precision;
-  const bool ffn_ln = pl.precision == CSE_BF16 && ffn_fused_enabled() && ffn_ln_fused_enabled() &&
-                      !ln_qkv_fused_enabled() && !outproj_ln_fused_enabled();
+  const bool ffn_ln = ffn_ln_path(pl);
   for (int l = 0; l < CSE_LAYERS; ++l) {
     const cse_layer_params& lp = sp.layer[l];
-    if (ffn_ln && l > 0 && ffn_ln_mode() == 1) {
+    if (ffn_ln && ffn_ln_mode() == 1 && (l > 0 || h_ready)) {
       // norm1(R) is already in H: the previous layer's feed-forward kernel wrote it
       if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
                  3 * kN, kN, 0, 0, st)) return 1;
@@ -332,15 +337,21 @@ static int masknet_impl(const cse_params* p, const void* E, int n_parts, const f
     }
   }
 
-  if (launch_build_sequences(XA, tok(0, 0), p->block[0].intra.pe, B, S, c, 0, Ra, st)) return 1;
+  // In the 4-launch layer mode (norm1 of layers 1-7 comes from the previous layer's feed-forward kernel) the kernel
+  // that BUILDS a stack's residual stream also writes norm1 of its first layer: no standalone LayerNorm launch is left
+  const bool h1 = ffn_ln_path(pl) && ffn_ln_mode() == 1;
+  bf16* Hn = h1 ? (bf16*)(ws + pl.H) : nullptr;
+  if (launch_build_sequences(XA, tok(0, 0), p->block[0].intra.pe, B, S, c, 0, Ra, st,
+                             p->block[0].intra.layer[0].ln1_g, p->block[0].intra.layer[0].ln1_b, Hn)) return 1;
   for (int blk = 0; blk < CSE_BLOCKS; ++blk) {
     const cse_block_params& bp = p->block[blk];
     // intra: sequences = chunks (ContSep.py:474-502)
-    if (run_stack(pl, bp.intra, Ra, B * S, kK + c, ws, st)) return 1;
+    if (run_stack(pl, bp.intra, Ra, B * S, kK + c, ws, st, h1)) return 1;
     if (launch_stack_finish(Ra, bp.intra.final_g, bp.intra.final_b, bp.intra_norm_g, bp.intra_norm_b, XA,
-                            B, S, c, 0, XB, Rb, bp.inter.pe, tok(blk, 1), part, stat, st)) return 1;
+                            B, S, c, 0, XB, Rb, bp.inter.pe, tok(blk, 1), part, stat, st,
+                            bp.inter.layer[0].ln1_g, bp.inter.layer[0].ln1_b, Hn)) return 1;
     // inter: sequences = in-chunk positions (ContSep.py:506-531)
-    if (run_stack(pl, bp.inter, Rb, B * kK, S + c, ws, st)) return 1;
+    if (run_stack(pl, bp.inter, Rb, B * kK, S + c, ws, st, h1)) return 1;
     const bool last = blk == CSE_BLOCKS - 1;
     if (last && pred_head != nullptr) {
       if (launch_pred_head(Rb, bp.inter.final_g, bp.inter.final_b, B, S, c, pred_head, st)) return 1;
@@ -348,7 +359,9 @@ static int masknet_impl(const cse_params* p, const void* E, int n_parts, const f
     if (launch_stack_finish(Rb, bp.inter.final_g, bp.inter.final_b, bp.inter_norm_g, bp.inter_norm_b, XB,
                             B, S, c, 1, XA, last ? nullptr : Ra,
                             last ? nullptr : p->block[blk + 1].intra.pe,
-                            last ? nullptr : tok(blk + 1, 0), part, stat, st)) return 1;
+                            last ? nullptr : tok(blk + 1, 0), part, stat, st,
+                            last ? nullptr : p->block[blk + 1].intra.layer[0].ln1_g,
+                            last ? nullptr : p->block[blk + 1].intra.layer[0].ln1_b, last ? nullptr : Hn)) return 1;
   }
 
   // mask head (ContSep.py:244-266) with the overlap-add commuted in front of conv2d

@@ -204,7 +204,7 @@ static int launch_relu_bwd_mixed(const bf16* F, float* d, size_t n, cudaStream_t
 }
 
 struct LayerWs16 {
-  bf16 *H, *QKV, *AO, *F1;
+  bf16 *H, *H1, *QKV, *AO, *F1;   // H: norm2 output, H1: norm1 output (kept for in_proj's weight gradient)
   float *Rmid, *dBig, *dH, *QKV32, *AO32;
   char* lin;          // scratch of cse_linear_bwd_tc, sized for the largest of the four linears
   size_t lin_bytes, total;
@@ -219,6 +219,7 @@ static LayerWs16 carve_layer_ws16(char* ws, size_t M) {
     return p;
   };
   w.H = (bf16*)take(M * kN * 2);
+  w.H1 = (bf16*)take(M * kN * 2);
   w.QKV = (bf16*)take(M * 3 * kN * 2);
   w.AO = (bf16*)take(M * kN * 2);
   w.F1 = (bf16*)take(M * kFfn * 2);
@@ -263,8 +264,8 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
   const size_t row_bytes = (size_t)M * kN * sizeof(float);
 
   // ---- recompute in the performance mode (the launch sequence of abi.cu:run_stack with the unfused FFN) ----
-  if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
-  if (launch_gemm_tc(w.H, kN, (const bf16*)p->in_proj_w_bf16, p->in_proj_b, 1.f, nullptr, w.QKV, 3 * kN, M, 3 * kN, kN, 0, 0, st)) return 1;
+  if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H1, st)) return 1;
+  if (launch_gemm_tc(w.H1, kN, (const bf16*)p->in_proj_w_bf16, p->in_proj_b, 1.f, nullptr, w.QKV, 3 * kN, M, 3 * kN, kN, 0, 0, st)) return 1;
   if (launch_attention(w.QKV, nseq, n, CSE_BF16, w.AO, st)) return 1;
   CSE_CUDA(cudaMemcpyAsync(w.Rmid, R_in, row_bytes, cudaMemcpyDeviceToDevice, st));
   if (launch_gemm_tc(w.AO, kN, (const bf16*)p->out_proj_w_bf16, p->out_proj_b, 1.f, w.Rmid, w.Rmid, kN, M, kN, kN, 0, 1, st)) return 1;
@@ -295,8 +296,8 @@ int cse_layer_bwd_bf16(const cse_layer_params* p, const cse_layer_grads* g, cons
     if (launch_bf16_to_f32(w.AO, w.AO32, (size_t)M * kN, st)) return 1;
     if (launch_attention_bwd(w.QKV32, w.AO32, w.dH, nseq, n, dQKV, st)) return 1;
   }
-  if (launch_layernorm(R_in, p->ln1_g, p->ln1_b, M, 1e-6f, CSE_BF16, w.H, st)) return 1;
-  if (linear_bwd_tc(w.H, 1, kN, p->in_proj_w, (const bf16*)p->in_proj_w_bf16, dQKV, nullptr, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
+  // (norm1's output is still in H1 from the recompute above)
+  if (linear_bwd_tc(w.H1, 1, kN, p->in_proj_w, (const bf16*)p->in_proj_w_bf16, dQKV, nullptr, M, 3 * kN, kN, w.dH, 1, kN, g->in_proj_w, g->in_proj_b, w.lin,
                         w.lin_bytes, stream)) return 1;
   return launch_layernorm_bwd(R_in, p->ln1_g, w.dH, M, 1e-6f, dR, 1, g->ln1_g, g->ln1_b, st);
 }

@@ -254,8 +254,10 @@ int launch_gn_stats(const void* x, int B, int rows, int act, float* gn_part, int
 int launch_gn_apply(const void* x, const float* stat, const float* g, const float* b, int B, int L,
                     int act, void* out, cudaStream_t st);
 int launch_segment(const float* x0, int B, int L, int S, float* X, cudaStream_t st);
+// ln_g / ln_b / H (optional): also write norm1 of the stack's first layer (bf16) for every row
 int launch_build_sequences(const float* X, const float* ctok, const float* pe, int B, int S, int c,
-                           int inter, float* R, cudaStream_t st);
+                           int inter, float* R, cudaStream_t st, const float* ln_g = nullptr,
+                           const float* ln_b = nullptr, bf16* H = nullptr);
 int launch_context_map(const float* ctx, const float* w, const float* b, int rows, int in_dim,
                        float* out, cudaStream_t st);
 // norm.cu
@@ -265,7 +267,8 @@ constexpr int kFinishParts = 64;  // GroupNorm partials per sample in stack_fini
 int launch_stack_finish(const float* R, const float* ln_g, const float* ln_b, const float* gn_g,
                         const float* gn_b, const float* skip, int B, int S, int c, int inter,
                         float* out, float* next_R, const float* next_pe, const float* next_ctok,
-                        float* gn_part, float* stat, cudaStream_t st);
+                        float* gn_part, float* stat, cudaStream_t st, const float* next_ln_g = nullptr,
+                        const float* next_ln_b = nullptr, bf16* next_H = nullptr);
 int launch_pred_head(const float* R, const float* ln_g, const float* ln_b, int B, int S, int c,
                      float* out, cudaStream_t st);
 // gemm_simt.cu / gemm_tc.cu

@@ -473,7 +473,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       if constexpr (LNF) {
         LN_STAMP(warp == 10 && it < 32, 4 * it + 1);
-        if (ln.H1 != nullptr && !(ln.dbg & 2)) {
+        if (ln.H1 != nullptr && !(ln.dbg & 2) && mpi + npairs < m_pairs) {   // (the last tile: all warps, below)
           // norm1 of the next layer on the 32 rows this warp has just updated: its own reduce-adds have completed
           // (wait_group without .read), the rows come back from L2
           if (lane == 0) {
@@ -489,6 +489,20 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     if (lane == 0) bulk_wait_all();  // all residual updates complete before the CTA retires
     __syncwarp();
+  }
+
+  if constexpr (LNF) {
+    // The CTA's LAST tile: nothing is left to overlap its norm1 rows with, so all fourteen non-pipe warps share them
+    // (one 8- or 16-row trip each instead of four trips by the output warps: the kernel's tail).  The output warps
+    // arrive after their reduce-adds have completed (bulk_wait_all above, which also invalidates L1).
+    if (ln.H1 != nullptr && !(ln.dbg & 2) && warp >= 2) {
+      named_bar_sync(8, 14 * 32);
+      const int n_mine = (m_pairs - pair_id + npairs - 1) / npairs;
+      const int m0 = (2 * pair_at(pair_id + (n_mine - 1) * npairs) + rank) * 128;
+      const int w = warp - 2;
+      if (w < 12) ln_rows_bf16(ln.R, M, m0 + w * 8, 8, ln.g1n, ln.b1n, ln.eps, ln.H1, lane);
+      else ln_rows_bf16(ln.R, M, m0 + 96 + (w - 12) * 16, 16, ln.g1n, ln.b1n, ln.eps, ln.H1, lane);
+    }
   }
 
   fence_before();

@@ -231,13 +231,21 @@ int launch_segment(const float* x0, int B, int L, int S, float* X, cudaStream_t 
 __global__ void __launch_bounds__(256) build_seq_kernel(const float* __restrict__ X,
                                                         const float* __restrict__ ctok,
                                                         const float* __restrict__ pe, int B, int S,
-                                                        int c, int inter, float* __restrict__ R) {
+                                                        int c, int inter, float* __restrict__ R,
+                                                        const float* __restrict__ ln_g,
+                                                        const float* __restrict__ ln_b, bf16* __restrict__ H) {
+  // H != NULL: also norm1 of the stack's first layer on every row (it is in the warp's registers)
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * 8;
   const int n = (inter ? S : kK) + c;
   const int per_b = inter ? kK : S;  // sequences per sample
   const size_t rows = (size_t)B * per_b * n;
+  f8 lg, lb;
+  if (H != nullptr) {
+    lg = ld8(ln_g + lane * 8);
+    lb = ld8(ln_b + lane * 8);
+  }
   for (size_t r = warp; r < rows; r += nwarps) {
     const int pos = (int)(r % n);
     const size_t seq = r / n;
@@ -255,14 +263,18 @@ __global__ void __launch_bounds__(256) build_seq_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < 8; ++i) v.v[i] += p.v[i];
     st8(R + r * kN + lane * 8, v);
+    if (H != nullptr) {
+      ln_row(v, lg, lb, 1e-6f);
+      st8(H + r * kN + lane * 8, v);
+    }
   }
 }
 
 int launch_build_sequences(const float* X, const float* ctok, const float* pe, int B, int S, int c,
-                           int inter, float* R, cudaStream_t st) {
+                           int inter, float* R, cudaStream_t st, const float* ln_g, const float* ln_b, bf16* H) {
   const size_t rows = (size_t)B * (inter ? kK : S) * ((inter ? S : kK) + c);
   const int grid = (int)min((size_t)148 * 8, (rows + 7) / 8);
-  build_seq_kernel<<<grid, 256, 0, st>>>(X, ctok, pe, B, S, c, inter, R);
+  build_seq_kernel<<<grid, 256, 0, st>>>(X, ctok, pe, B, S, c, inter, R, ln_g, ln_b, H);
   return check_launch("build_seq_kernel");
 }
 

@@ -119,12 +119,20 @@ __global__ void __launch_bounds__(256) finish_apply_kernel(
     const float* __restrict__ gn_g, const float* __restrict__ gn_b, const float* __restrict__ skip,
     const float* __restrict__ stat, int B, int S, int c, int inter, float* __restrict__ out,
     float* __restrict__ next_R, const float* __restrict__ next_pe,
-    const float* __restrict__ next_ctok) {
+    const float* __restrict__ next_ctok, const float* __restrict__ next_ln_g,
+    const float* __restrict__ next_ln_b, bf16* __restrict__ next_H) {
+  // next_H != NULL: also norm1 of the next stack's first layer on every row written to next_R (the row is in the
+  // warp's registers: the stack's first layernorm_kernel launch and its 140 MB re-read disappear)
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * 8;
   const f8 lg = ld8(ln_g + lane * 8), lb = ld8(ln_b + lane * 8);
   const f8 gg = ld8(gn_g + lane * 8), gb = ld8(gn_b + lane * 8);
+  f8 ng, nb;
+  if (next_H != nullptr) {
+    ng = ld8(next_ln_g + lane * 8);
+    nb = ld8(next_ln_b + lane * 8);
+  }
   const size_t rows = (size_t)B * S * kK;
   const int next_inter = !inter;
   // two rows per trip: the four loads (R row and skip row of both) are in flight together — the kernel's 86
@@ -163,6 +171,10 @@ __global__ void __launch_bounds__(256) finish_apply_kernel(
 #pragma unroll
         for (int i = 0; i < 8; ++i) w.v[i] = v.v[i] + p.v[i];
         st8(next_R + stack_row(b, s, k, S, c, next_inter) * kN + lane * 8, w);
+        if (next_H != nullptr) {
+          ln_row(w, ng, nb, 1e-6f);
+          st8(next_H + stack_row(b, s, k, S, c, next_inter) * kN + lane * 8, w);
+        }
         // the warp that owns the first audio row of a next-stack sequence also writes its prompt
         const bool first = next_inter ? (s == 0) : (k == 0);
         if (first) {
@@ -173,6 +185,10 @@ __global__ void __launch_bounds__(256) finish_apply_kernel(
 #pragma unroll
             for (int i = 0; i < 8; ++i) t.v[i] += pj.v[i];
             st8(next_R + (base + j) * kN + lane * 8, t);
+            if (next_H != nullptr) {
+              ln_row(t, ng, nb, 1e-6f);
+              st8(next_H + (base + j) * kN + lane * 8, t);
+            }
           }
         }
       }
@@ -183,7 +199,8 @@ __global__ void __launch_bounds__(256) finish_apply_kernel(
 int launch_stack_finish(const float* R, const float* ln_g, const float* ln_b, const float* gn_g,
                         const float* gn_b, const float* skip, int B, int S, int c, int inter,
                         float* out, float* next_R, const float* next_pe, const float* next_ctok,
-                        float* gn_part, float* stat, cudaStream_t st) {
+                        float* gn_part, float* stat, cudaStream_t st, const float* next_ln_g,
+                        const float* next_ln_b, bf16* next_H) {
   dim3 g1(kFinishParts, B);
   finish_stats_kernel<<<g1, 256, 0, st>>>(R, ln_g, ln_b, S, c, inter, gn_part);
   if (check_launch("finish_stats_kernel")) return 1;
@@ -195,7 +212,8 @@ int launch_stack_finish(const float* R, const float* ln_g, const float* ln_b, co
   }
   const int grid = (int)min((size_t)148 * 8, (rows + 7) / 8);
   finish_apply_kernel<<<grid, 256, 0, st>>>(R, ln_g, ln_b, gn_g, gn_b, skip, stat, B, S, c, inter,
-                                            out, next_R, next_pe, next_ctok);
+                                            out, next_R, next_pe, next_ctok, next_ln_g, next_ln_b,
+                                            next_R != nullptr ? next_H : nullptr);
   return check_launch("finish_apply_kernel");
 }
 
