@@ -313,9 +313,11 @@ def attention_flops_per_forward(ps):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class (tcgen05 GEMMs), from the
-# ncu --set full capture in profiles/r01_ncu_full_layer.txt: mean over the three launches of an intra layer
-# (QKV 223 MB, out-proj 291 MB, fused FFN 291 MB).  A committed measurement, not something bench.py can re-measure.
-GEMM_CLASS_DRAM_BYTES_PER_LAUNCH = 2.682e8
+# ncu --set full capture in profiles/r02_ncu_kernels.txt section (a): mean over the three GEMM-class launches of an
+# intra and an inter layer (QKV 222 / 229 MB, out-proj 293 / 299 MB, feed-forward kernel with the layer's LayerNorms
+# 467 / 480 MB; algorithmic 280 + 350 + 350 MB of GEMM traffic + 2 x 210 MB of LayerNorm traffic, part of it L2-only).
+# A committed measurement, not something bench.py can re-measure.
+GEMM_CLASS_DRAM_BYTES_PER_LAUNCH = 3.317e8
 
 
 def run_ours(args):
@@ -450,7 +452,8 @@ def run_ours(args):
         achieved = flops_per_launch / (g_ms / g_n * 1e-3) / 1e12
         a_ms = ms_cls[1] / args.steps
         roofline = {
-            "kernel": "cse::gemm_tc_kernel + cse::ffn_tc_kernel (tcgen05 + TMA bf16 GEMMs: all Linear / 1x1-conv layers, fused FFN)",
+            "kernel": "cse::gemm_tc_kernel + cse::ffn_tc_kernel (tcgen05 + TMA bf16 GEMMs: all Linear / 1x1-conv layers; the fused "
+                      "FFN kernel also carries the layer's two LayerNorms, whose time counts here while their work is not FLOPs)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS)",
             "traffic": GEMM_CLASS_DRAM_BYTES_PER_LAUNCH,
