@@ -567,6 +567,7 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     model = model.to(dev).train()
     model.precision = None if amp else "fp32"
     net = model
+    cap_stream = None
     if world > 1:   # the reference's own wrapper (train_ContExt.py:269-273): bucketed NCCL all-reduce overlapped with backward
         ddp_kw = {}
         if args.ddp_bucket_view:
@@ -575,8 +576,16 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
             ddp_kw["bucket_cap_mb"] = args.ddp_bucket_mb
         if args.ddp_static_graph:
             ddp_kw["static_graph"] = True
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
-                                                        find_unused_parameters=False, **ddp_kw)
+        if args.train_graph == "ddp":   # (opt-in) DDP built on the stream its warm-up iterations and the capture use
+            cap_stream = torch.cuda.Stream()
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap_stream):
+                net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                                find_unused_parameters=False, **ddp_kw)
+            torch.cuda.current_stream().wait_stream(cap_stream)
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                            find_unused_parameters=False, **ddp_kw)
     fused_opt = args.train_optim == "fused"
     if fused_opt:   # clip_grad_norm_ + AdamW(amsgrad) in three launches (cse_optim_step), no host sync on the norm
         from cse_b200.optim import AdamW as FusedAdamW
@@ -683,9 +692,15 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     # (runtime.GraphedStep) — run eagerly its ~1000 short launches are bound by the launching host thread.  A
     # DistributedDataParallel step (N > 1) stays eager.
     graphed = None
-    if world == 1 and fused_opt and args.train_graph != "off":
+    ms_eager = None
+    if world > 1 and args.train_graph == "ddp":
+        ms_e, _ = timed(step_device, steps)          # the eagerly launched DDP step, for the comm block below
+        ms_eager = ms_e / steps
+    if fused_opt and ((world == 1 and args.train_graph != "off") or (world > 1 and args.train_graph == "ddp")):
         from cse_b200.runtime import GraphedStep
-        graphed = GraphedStep(lambda m, c, t: step(m, c, t), mix_d, ctx_d, tgt_d, warmup=3)
+        # (DDP: eleven warm-up iterations before the capture, as torch's CUDA-graph notes ask for)
+        graphed = GraphedStep(lambda m, c, t: step(m, c, t), mix_d, ctx_d, tgt_d, warmup=3 if world == 1 else 11,
+                              stream=cap_stream)
 
         def step_device():                                                   # noqa: F811
             return graphed(mix_d, ctx_d, tgt_d)
@@ -704,7 +719,11 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
     e2e_value = audio_s / (wall / steps)
     comm = None
     if world > 1:
-        ms_nosync, _ = timed(step_no_allreduce, steps)
+        # (with a captured DDP step the no_sync() comparison is not taken: DDP's eager no_sync bookkeeping after a
+        # capture is not what the graph replays; the eager step measured before the capture is reported beside it)
+        ms_nosync = None
+        if graphed is None:
+            ms_nosync, _ = timed(step_no_allreduce, steps)
         flat = torch.zeros(n_params, dtype=torch.float32, device=dev)
 
         def allreduce_alone():   # the same bytes in DDP's default 25 MB buckets, nothing else running
@@ -712,13 +731,14 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
                 dist.all_reduce(chunk)
 
         ms_ar, _ = timed(allreduce_alone, steps)
-        exposed = max(0.0, ms_step - ms_nosync / steps)
         alone = ms_ar / steps
+        exposed = max(0.0, ms_step - ms_nosync / steps) if ms_nosync is not None else None
         comm = {"collective": "NCCL all-reduce of fp32 gradients (stock DistributedDataParallel"
                               + (f", {ddp_kw}" if ddp_kw else ", default arguments as train_ContExt.py:269-273: 25 MB buckets") + ")",
-                "allreduce_bytes_per_step": n_params * 4, "step_ms": ms_step, "step_ms_without_allreduce": ms_nosync / steps,
+                "allreduce_bytes_per_step": n_params * 4, "step_ms": ms_step, "step_ms_eager": ms_eager,
+                "step_ms_without_allreduce": ms_nosync / steps if ms_nosync is not None else None,
                 "exposed_allreduce_ms": exposed, "allreduce_alone_ms": alone,
-                "overlap_fraction": max(0.0, min(1.0, 1.0 - exposed / alone)) if alone > 0 else None}
+                "overlap_fraction": max(0.0, min(1.0, 1.0 - exposed / alone)) if (alone > 0 and exposed is not None) else None}
     clocks = sampler.summary() if rank == 0 else None
     if rank != 0:
         return None
@@ -745,7 +765,9 @@ def measure_train(args, world, rank, local, dev, steps, quiet=False):
                    "sharding": f"dp{world}: stock DistributedDataParallel, NCCL gradient all-reduce overlapped with backward",
                    "l2": "no flush: one step streams several GB of activations through a 126 MB L2"},
         "clocks": clocks, "loss": loss0, "n_params": n_params, "comm": comm,
-        "step_execution": ("one CUDA graph replay per step (cse_b200.runtime.GraphedStep)" if graphed is not None
+        "step_execution": ("one CUDA graph replay per step (cse_b200.runtime.GraphedStep)"
+                           + (", DistributedDataParallel's NCCL all-reduce captured inside" if world > 1 else "")
+                           if graphed is not None
                            else "eager launches (DistributedDataParallel step)" if world > 1 else "eager launches"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() + ctx_h.numel() + tgt_h.numel()) * 4,
                 "d2h_bytes_per_step": 4, "api": "model(mix, ctx) -> loss.backward() -> optimizer.step() from pinned host buffers"},
@@ -766,6 +788,8 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.train_graph == "ddp":   # whole-step capture with the NCCL all-reduce inside (torch's CUDA-graph notes)
+            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
         dist.init_process_group("nccl", device_id=dev)
     res = measure_train(args, world, rank, local, dev, steps=args.steps)
     if rank == 0:
@@ -796,8 +820,9 @@ def main():
                     help="training leg: torch.autocast(bf16) like the reference's --bf16 (tensor-core layers), or the fp32 parity kernels")
     ap.add_argument("--train-ragged", action="store_true",
                     help="training leg: DailyTalk-like lengths U(1.5 s, 8 s) right-padded to the batch max instead of fixed --train-seconds")
-    ap.add_argument("--train-graph", default="auto", choices=["auto", "off"],
-                    help="training leg at N = 1: replay the whole step as one CUDA graph (auto) or launch it eagerly (off)")
+    ap.add_argument("--train-graph", default="auto", choices=["auto", "off", "ddp"],
+                    help="training leg: auto = replay the whole step as one CUDA graph at N = 1, eager DDP steps at N > 1; "
+                         "off = always eager; ddp = (opt-in, --workload train) also capture the DistributedDataParallel step at N > 1")
     ap.add_argument("--no-train", action="store_true", help="forward workload: skip the `train` sub-object")
     ap.add_argument("--ddp-bucket-view", action="store_true", help="training leg, N > 1: DDP(gradient_as_bucket_view=True) (A/B; the reference uses the defaults)")
     ap.add_argument("--ddp-bucket-mb", type=int, default=0, help="training leg, N > 1: DDP(bucket_cap_mb=...) (A/B; default 25)")

@@ -52,9 +52,9 @@ class GraphedStep:
     optimiser of this package (or a capturable torch optimiser); `fn` runs `warmup` times eagerly first.  Single
     process per graph: a DistributedDataParallel step is not captured here."""
 
-    def __init__(self, fn, *static_args, warmup=3):
+    def __init__(self, fn, *static_args, warmup=3, stream=None):
         self.args = static_args
-        side = torch.cuda.Stream()
+        side = stream if stream is not None else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
