@@ -336,6 +336,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not args.no_train and args.train_graph == "auto":   # the DDP step is captured into a CUDA graph (see below)
+            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -467,11 +469,14 @@ def run_ours(args):
                            "unit": "TFLOP/s", "frac": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]},
         }
 
-    # The training leg runs BEFORE the legs that use the host cores (parity oracle, CPU baseline: 16 intra-op threads
-    # whose pool keeps spinning afterwards): its step is close to host launch-bound (~1000 launches per 18 ms) and
-    # measured 27 ms instead of 18 ms when it ran after them.
+    # N = 1: the training leg runs BEFORE the legs that use the host cores (parity oracle, CPU baseline: 16 intra-op
+    # threads whose pool keeps spinning afterwards); an eagerly launched step measured 27 ms instead of 18 ms after them.
+    # N > 1: it runs LAST, as one captured CUDA graph per rank with DistributedDataParallel's all-reduce inside (a
+    # replay does not care about the host) and under a watchdog: everything else of the line is measured by then, and if
+    # the capture or a replay hangs at this N the line is printed without the training measurement instead of not at all.
     train = None
-    if not args.no_train:
+    train_last = world > 1 and not args.no_train and args.train_graph == "auto"
+    if not args.no_train and not train_last:
         train = measure_train(args, world, rank, local, dev, steps=max(3, min(args.steps, 10)), quiet=True)
 
     parity = None
@@ -488,7 +493,9 @@ def run_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"1 of the 16 mixtures ({SECONDS} s) per forward, 3 timed forwards + 1 warm-up, fp32, the reference's op sequence on stock torch modules, {cores} threads"}
 
-    if rank == 0:
+    def emit(train_obj):
+        if rank != 0:
+            return
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -501,12 +508,40 @@ def run_ours(args):
                                       "api": "Sepformer.host_pipeline -> cse_pipeline_submit / cse_pipeline_wait (pinned host buffers, 2 steps in flight, every step's H2D and D2H inside the timed region)",
                                       "blocking_call_value": e2e_blocking,
                                       "blocking_call_api": "Sepformer.separate_host -> cse_forward_host (one blocking call per step)"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "train": train,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "train": train_obj,
         }), flush=True)
+
+    if train_last:
+        import threading
+        dist.barrier()
+        torch.cuda.synchronize()
+        finished = threading.Event()
+
+        def watchdog():
+            if not finished.wait(TRAIN_WATCHDOG_S):
+                emit({"error": f"the captured DistributedDataParallel step did not finish within {TRAIN_WATCHDOG_S} s at N = {world}: "
+                               "no training measurement on this line"})
+                sys.stdout.flush()
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        failed = None
+        try:
+            args.train_graph = "ddp"
+            train = measure_train(args, world, rank, local, dev, steps=max(3, min(args.steps, 10)), quiet=True)
+        except Exception as e:      # (a rank that fails alone leaves the others in a collective: their watchdogs end them)
+            failed = repr(e)
+        finished.set()
+        if failed is not None:
+            emit({"error": "training leg failed: " + failed})
+            sys.stdout.flush()
+            os._exit(0)
+    emit(train)
     if world > 1:
         dist.destroy_process_group()
 
 
+TRAIN_WATCHDOG_S = 300
 TRAIN_BATCH = 2
 
 
@@ -821,8 +856,10 @@ def main():
     ap.add_argument("--train-ragged", action="store_true",
                     help="training leg: DailyTalk-like lengths U(1.5 s, 8 s) right-padded to the batch max instead of fixed --train-seconds")
     ap.add_argument("--train-graph", default="auto", choices=["auto", "off", "ddp"],
-                    help="training leg: auto = replay the whole step as one CUDA graph at N = 1, eager DDP steps at N > 1; "
-                         "off = always eager; ddp = (opt-in, --workload train) also capture the DistributedDataParallel step at N > 1")
+                    help="training leg: auto = the whole step replays as one CUDA graph (N = 1 always; N > 1: in the default "
+                         "forward workload's `train` sub-object, captured with DistributedDataParallel's all-reduce inside "
+                         "and run last under a watchdog; `--workload train` at N > 1 stays eager so that its no_sync() "
+                         "comparison can be taken); off = always eager; ddp = capture the DDP step in `--workload train` too")
     ap.add_argument("--no-train", action="store_true", help="forward workload: skip the `train` sub-object")
     ap.add_argument("--ddp-bucket-view", action="store_true", help="training leg, N > 1: DDP(gradient_as_bucket_view=True) (A/B; the reference uses the defaults)")
     ap.add_argument("--ddp-bucket-mb", type=int, default=0, help="training leg, N > 1: DDP(bucket_cap_mb=...) (A/B; default 25)")
