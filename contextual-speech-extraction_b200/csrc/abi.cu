@@ -207,14 +207,17 @@ static bool outproj_ln_fused_enabled() {
 // The two LayerNorms of a layer ride along in the feed-forward kernel (ffn_tc.cu, LNF variant): norm2 in its own
 // LayerNorm warps ahead of the tensor pipe, norm1 of the NEXT layer in its output warps — four launches per layer.
 // CSE_FFN_LN=0 keeps the separate layernorm_kernel launches (A/B aid).
-static int ffn_ln_mode() {   // 0: off, 1: norm2 + next norm1 (default), 2: norm2 only (norm1 stays a launch)
+static int ffn_ln_mode() {   // 0: off, 1: norm2 + next norm1, 2: norm2 only (norm1 stays a launch), 3: auto (default)
   static const int mode = []() {
     const char* e = getenv("CSE_FFN_LN");
-    return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+    return e == nullptr ? 3 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }();
   return mode;
 }
-static bool ffn_ln_fused_enabled() { return ffn_ln_mode() != 0; }
+// auto: the LayerNorms ride in the feed-forward kernel when its CTAs have several row tiles each to hide them behind
+// (>= 16 k rows: +7-10 % on the forward); with one tile per CTA they are latency in front of and behind the tile and
+// the separate launches are 5-10 % faster (profiles/r02_sweep_cfg4_cfg5.md)
+constexpr size_t kFfnLnMinRows = 16000;
 
 // CSE_LN_FUSED=1 runs norm1 -> in_proj as one kernel (gemm_ln_tc.cu).  Off by default: measured 123-132 us
 // against 36 + 67 us for the two kernels (its LayerNorm warps cannot keep enough loads in flight inside the
@@ -228,9 +231,11 @@ static bool ln_qkv_fused_enabled() {
 }
 
 static bool ffn_ln_path(const Plan& pl) {
-  return pl.precision == CSE_BF16 && ffn_fused_enabled() && ffn_ln_fused_enabled() && !ln_qkv_fused_enabled() &&
-         !outproj_ln_fused_enabled();
+  const int mode = ffn_ln_mode();
+  return pl.precision == CSE_BF16 && ffn_fused_enabled() && mode != 0 && (mode != 3 || pl.m_max >= kFfnLnMinRows) &&
+         !ln_qkv_fused_enabled() && !outproj_ln_fused_enabled();
 }
+static bool ffn_ln_next_norm1() { return ffn_ln_mode() != 2; }   // (mode 2: A/B aid, norm1 stays a launch)
 
 // SBTransformerBlock_CSE body after the PE add: 8 pre-norm layers on the fp32 residual stream R
 // (TransformerEncoderLayer.forward, CSE_transformer.py:385-416).  The final LayerNorm belongs to
@@ -247,7 +252,7 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
   const bool ffn_ln = ffn_ln_path(pl);
   for (int l = 0; l < CSE_LAYERS; ++l) {
     const cse_layer_params& lp = sp.layer[l];
-    if (ffn_ln && ffn_ln_mode() == 1 && (l > 0 || h_ready)) {
+    if (ffn_ln && ffn_ln_next_norm1() && (l > 0 || h_ready)) {
       // norm1(R) is already in H: the previous layer's feed-forward kernel wrote it
       if (linear(pl, H, kN, lp.in_proj_w, lp.in_proj_w_bf16, lp.in_proj_b, 1.f, nullptr, QKV, 3 * kN, M,
                  3 * kN, kN, 0, 0, st)) return 1;
@@ -276,7 +281,7 @@ static int run_stack(const Plan& pl, const cse_stack_params& sp, float* R, int n
       // norm2 -> Linear -> ReLU -> Linear -> +R -> next layer's norm1, one kernel; AO (consumed by out_proj) is the
       // scratch that receives norm2(R)
       CSE_REQUIRE(lp.ffn1_w_bf16 && lp.ffn2_w_bf16, "bf16 weights missing: call cse_pack_bf16 first");
-      const cse_layer_params* nx = l + 1 < CSE_LAYERS && ffn_ln_mode() == 1 ? &sp.layer[l + 1] : nullptr;
+      const cse_layer_params* nx = l + 1 < CSE_LAYERS && ffn_ln_next_norm1() ? &sp.layer[l + 1] : nullptr;
       if (launch_ffn_tc_ln(R, lp.ln2_g, lp.ln2_b, 1e-6f, (bf16*)AO, (const bf16*)lp.ffn1_w_bf16, lp.ffn1_b,
                            (const bf16*)lp.ffn2_w_bf16, lp.ffn2_b, nx ? nx->ln1_g : nullptr,
                            nx ? nx->ln1_b : nullptr, nx ? (bf16*)H : nullptr, M, st)) return 1;
@@ -339,7 +344,7 @@ static int masknet_impl(const cse_params* p, const void* E, int n_parts, const f
 
   // In the 4-launch layer mode (norm1 of layers 1-7 comes from the previous layer's feed-forward kernel) the kernel
   // that BUILDS a stack's residual stream also writes norm1 of its first layer: no standalone LayerNorm launch is left
-  const bool h1 = ffn_ln_path(pl) && ffn_ln_mode() == 1;
+  const bool h1 = ffn_ln_path(pl) && ffn_ln_next_norm1();
   bf16* Hn = h1 ? (bf16*)(ws + pl.H) : nullptr;
   if (launch_build_sequences(XA, tok(0, 0), p->block[0].intra.pe, B, S, c, 0, Ra, st,
                              p->block[0].intra.layer[0].ln1_g, p->block[0].intra.layer[0].ln1_b, Hn)) return 1;

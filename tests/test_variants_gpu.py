@@ -2,7 +2,8 @@
 process) produce the same results as the default path.  Each variant runs in a fresh interpreter:
 the bf16 golden-vector tests of test_forward_gpu.py plus the tensor-core GEMM tests.
 
-CSE_FFN_LN=0        separate layernorm_kernel launches instead of the LayerNorm warps of the feed-forward kernel
+CSE_FFN_LN=0 / 1    separate layernorm_kernel launches / the LayerNorm warps of the feed-forward kernel at every size
+                    (default: the latter from 16 k rows up, so the small golden fixtures need the switch to reach it)
 CSE_FFN_FUSED=0     two-GEMM feed-forward instead of the fused kernel (ffn_tc.cu)
 CSE_LN_FUSED=1      norm1 -> in_proj as one kernel (gemm_ln_tc.cu)
 CSE_OUTPROJ_LN=1    out-proj + residual + norm2 as one kernel (gemm_tc.cu, LayerNorm epilogue)
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"CSE_FFN_LN": "0"}, {"CSE_FFN_FUSED": "0"}, {"CSE_LN_FUSED": "1"}, {"CSE_OUTPROJ_LN": "1"},
+@pytest.mark.parametrize("env", [{"CSE_FFN_LN": "0"}, {"CSE_FFN_LN": "1"}, {"CSE_FFN_FUSED": "0"}, {"CSE_LN_FUSED": "1"}, {"CSE_OUTPROJ_LN": "1"},
                                  {"CSE_ATTN_VER": "4", "CSE_DECODE_SIMT": "1"}],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_matches_golden(env):
