@@ -14,14 +14,17 @@ e2e    : same metric through the host-buffer C-ABI entry: pinned host mixtures -
 parity : mixtures 0 and 15 of the timed batch checked against the CPU oracle outside the timed region.
 train  : BASELINE configs[2] measured in the same process (ContExt forward + -SI-SNR + backward + DDP gradient
          all-reduce + clip + AdamW under autocast, 2 mixtures x 4 s per GPU) so that the driver's 1 -> 8 GPU runs
-         time the one collective this path has.
+         time the one collective this path has.  The whole step replays as ONE CUDA graph per rank
+         (cse_b200.runtime.GraphedStep; at N > 1 with DistributedDataParallel's NCCL all-reduce captured inside, run
+         last and under a watchdog so that a capture problem costs this sub-object, not the line).
 roofline / cpu_baseline: see DESIGN.md §Measurement.
 --impl reference: the reference's CPU path — its op sequence on the stock torch modules it instantiates
 (oracle/eager_reference.py; the Python reference itself cannot travel to the GPU box), all host threads, one 4 s
 mixture per step.
---workload train (not the driver's default): BASELINE configs[2] — ContExt forward + -SI-SNR loss +
-backward + gradient all-reduce (stock DDP over NCCL) + clip + AdamW, 2 mixtures x 4 s per GPU, fp32
-parity-mode kernels (the bf16 tensor-core backward is not built yet).
+--workload train (not the driver's default): BASELINE configs[2] on its own line — ContExt forward + -SI-SNR loss +
+backward + gradient all-reduce (stock DDP over NCCL) + clip + AdamW, 2 mixtures x 4 s per GPU, under torch.autocast
+(bf16 tensor-core forward / recompute / dgrad / wgrad / attention backward; --train-precision fp32 = the parity
+kernels); --train-graph off | auto | ddp, --train-ragged, --train-seconds, --train-loss pit.
 """
 import argparse
 import ctypes as C
