@@ -445,16 +445,29 @@ def run_ours(args):
         for _ in range(args.steps):
             step_device()
         torch.cuda.synchronize()
-        ms_cls = (C.c_double * 4)()
-        n_cls = (C.c_longlong * 4)()
-        _lib.call("cse_profile_collect", ms_cls, n_cls, 4)
+        ms_cls = (C.c_double * 5)()
+        n_cls = (C.c_longlong * 5)()
+        _lib.call("cse_profile_collect", ms_cls, n_cls, 5)
         lib.cse_profile_enable(0)
+        # the GEMM class = gemm_tc_kernel launches (slot 0) + the fused feed-forward kernel (slot 4)
+        f_ms, f_n = ms_cls[4] / args.steps, n_cls[4] // args.steps
+        ms_cls[0] += ms_cls[4]
+        n_cls[0] += n_cls[4]
         names = ["tcgen05_gemm", "attention", "layernorm", "simt_gemm"]
         share = {names[i]: {"ms_per_step": ms_cls[i] / args.steps, "launches_per_step": n_cls[i] // args.steps}
                  for i in range(4) if n_cls[i]}
         g_ms, g_n = ms_cls[0] / args.steps, max(1, n_cls[0] // args.steps)
         flops_per_launch = gemm_flops_per_forward(ps) / g_n
         achieved = flops_per_launch / (g_ms / g_n * 1e-3) / 1e12
+        dominant = None
+        if f_n:      # the step's dominant kernel on its own: Linear(256,1024) -> ReLU -> Linear(1024,256) (+ the layer's LayerNorms)
+            rows = ps.B * ps.S * ps.n_intra + ps.B * 250 * ps.n_inter            # rows of an intra + an inter stack
+            f_flops = 16 * rows * 4.0 * 256 * 1024 / f_n                         # 2 blocks x 8 layers per stack; 2 GEMMs x 2 FLOP per MAC
+            f_ach = f_flops / (f_ms / f_n * 1e-3) / 1e12
+            dominant = {"kernel": "cse::ffn_tc_kernel (fused feed-forward sub-block; from 16 k rows per stack up it also carries the layer's two LayerNorms)",
+                        "launches_per_step": int(f_n), "avg_launch_ms": f_ms / f_n, "share_of_step": f_ms / ms_step,
+                        "algorithmic_flops_per_launch": f_flops, "achieved": f_ach, "unit": "TFLOP/s",
+                        "frac": f_ach / peaks["tflops_sustained"]}
         a_ms = ms_cls[1] / args.steps
         roofline = {
             "kernel": "cse::gemm_tc_kernel + cse::ffn_tc_kernel (tcgen05 + TMA bf16 GEMMs: all Linear / 1x1-conv layers; the fused "
@@ -466,6 +479,7 @@ def run_ours(args):
             "avg_launch_ms": g_ms / g_n,
             "kernel_share_of_step": g_ms / ms_step,
             "classes": share,
+            "dominant_kernel": dominant,
             "attention": {"achieved": attention_flops_per_forward(ps) / (a_ms * 1e-3) / 1e12 if a_ms else None,
                           "unit": "TFLOP/s (QK^T + PV only; the kernels are bound by softmax / tcgen05.ld, not by the MMAs)"},
             "whole_step": {"achieved": shapes.algorithmic_flops(ps) / (ms_step * 1e-3) / 1e12,

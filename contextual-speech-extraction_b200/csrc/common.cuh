@@ -174,7 +174,7 @@ __device__ __forceinline__ void ln_row(f8& x, const f8& g, const f8& b, float ep
 }
 
 // ---- optional per-kernel-class device timing (bench.py roofline leg; off by default) ----
-enum KernelClass { kClsGemmTc = 0, kClsAttention = 1, kClsLayerNorm = 2, kClsGemmSimt = 3, kClsCount = 4 };
+enum KernelClass { kClsGemmTc = 0, kClsAttention = 1, kClsLayerNorm = 2, kClsGemmSimt = 3, kClsFfn = 4, kClsCount = 5 };
 struct KernelScope {  // records a CUDA event pair around the launches made in its lifetime
   KernelScope(int cls, cudaStream_t st);
   ~KernelScope();

@@ -542,7 +542,7 @@ static int launch_ffn_common(bool lnf, const bf16* A, const bf16* W1, const floa
   const int m_pairs = (ceil_div(M, 128) + 1) / 2;
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (m_pairs < max_pairs ? m_pairs : max_pairs);
-  KernelScope prof(kClsGemmTc, st);
+  KernelScope prof(kClsFfn, st);
   cudaError_t le = lnf ? launch_pdl(ffn_tc_kernel<true>, dim3(grid), dim3(kFfnLnThreads), kFfnSmem, st, 2, tmA, tmW1,
                                     tmW2, tmR, b1, b2, M, ln)
                        : launch_pdl(ffn_tc_kernel<false>, dim3(grid), dim3(kFfnThreads), kFfnSmem, st, 2, tmA, tmW1,

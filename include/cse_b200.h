@@ -119,7 +119,7 @@ CSE_API int cse_debug_force_mma_attention(int on);
  * pipeline events (tools/attn_trace.py); NULL turns it off. */
 CSE_API int cse_debug_attention_trace(long long* device_buffer);
 /* Optional device timing per kernel class (0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 fp32 SIMT
- * GEMM): while enabled, each launch of those classes is bracketed by a CUDA event pair on its
+ * GEMM, 4 fused feed-forward kernel — counted in class 0 when n_classes == 4): while enabled, each launch of those classes is bracketed by a CUDA event pair on its
  * stream; cse_profile_collect sums and clears them (synchronises on the recorded events). */
 CSE_API int cse_profile_enable(int on);
 CSE_API int cse_profile_collect(double* ms_by_class, long long* launches_by_class, int n_classes);
